@@ -1,0 +1,131 @@
+/*
+ * paro_b200.h -- C ABI of libparo_b200.so: the sm_100a (B200) implementation of ParoQuant's
+ * hot path (scaled pairwise rotation of the activations + AWQ INT4 group dequant + GEMV/GEMM).
+ *
+ * Plain pointers and sizes only; no torch / ATen types.  Every pointer named "device" must be
+ * device memory of the CUDA device that is current on the calling thread; `stream` is a
+ * cudaStream_t.  No entry point allocates, synchronises the host, or keeps mutable global
+ * state, so all of them are safe under CUDA-graph capture and re-entrant across streams (a
+ * `workspace` must not be shared by launches that may run concurrently).
+ *
+ * Each entry point replaces one piece of the reference's operator surface (paths relative to
+ * the z-lab/paroquant tree):
+ *
+ *   paro_rotate            torch.ops.rotation.rotate
+ *                            paroquant/kernels/cuda/rotation.cu:10-43   (kernel)
+ *                            paroquant/kernels/cuda/rotation.cu:62-95   (launcher, dtype casts)
+ *                            paroquant/kernels/cuda/rotation.cu:111-135 (dispatch + schema)
+ *   paro_packed_bytes /    the AWQ -> kernel-layout repack the reference does through Marlin in
+ *   paro_prepack             ParoQuantLinearMethod.process_weights_after_loading
+ *                            paroquant/inference/backends/vllm/plugin.py:208-279
+ *   paro_workspace_bytes   Marlin's per-layer workspace (plugin.py:249,272)
+ *   paro_linear_forward    ParoQuantLinearMethod.apply   plugin.py:281-311  (rotate + Marlin,
+ *                            per partition, cat, bias) and RotateQuantizedLinear.forward
+ *                            paroquant/inference/backends/transformers/modules.py:57-71
+ *   paro_last_error        TORCH_CHECK messages of rotation.cu:66,92,108,114,123
+ *
+ * Return value of every int function: 0 on success, a PARO_E* code otherwise; the message is
+ * available from paro_last_error() on the same thread.
+ */
+#ifndef PARO_B200_H_
+#define PARO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PARO_ABI_VERSION 1
+#define PARO_MAX_PARTS 8
+
+/* element types (activations, rotation parameters, scales) */
+#define PARO_F32 0
+#define PARO_F16 1
+#define PARO_BF16 2
+
+/* error codes */
+#define PARO_OK 0
+#define PARO_EINVAL 1      /* bad shape / dtype / null pointer / alignment */
+#define PARO_EUNSUPPORTED 2 /* valid request this build has no kernel for   */
+#define PARO_ECUDA 3       /* CUDA runtime error (message carries cudaGetErrorString) */
+#define PARO_EWORKSPACE 4  /* workspace too small */
+
+typedef void *paro_stream_t; /* cudaStream_t */
+
+/* Geometry of one (possibly merged) quantised linear as this rank sees it.
+ * Mirrors what ParoQuantLinearMethod.create_weights receives (plugin.py:173-206):
+ * in_features = input_size_per_partition, part_sizes = output_partition_sizes.        */
+typedef struct paro_linear_shape {
+  int32_t in_features;                 /* K, multiple of group_size                    */
+  int32_t out_features;                /* N = sum(part_sizes)                          */
+  int32_t group_size;                  /* quantisation == rotation group; 128          */
+  int32_t krot;                        /* rotations per group (1..16); 8 in checkpoints */
+  int32_t n_parts;                     /* 1, or 3 for QKV / 2 for gate_up              */
+  int32_t part_sizes[PARO_MAX_PARTS];  /* each a multiple of 16                        */
+  int32_t dtype;                       /* activation / output dtype: PARO_F16 | PARO_BF16 */
+} paro_linear_shape;
+
+int paro_abi_version(void);
+const char *paro_last_error(void);
+
+/* out[m, g*G + c] = (prod_r Givens_r)(x[m, g*G + :] * scales) -- torch.ops.rotation.rotate.
+ *   x, out      device [M, K] of `dtype` (F32 | F16 | BF16), contiguous; out may alias x
+ *   idx_ij      device [krot, K] int16, local pair indices (i at 2t, j at 2t+1)
+ *   theta       device [krot, K/2] of theta_dtype; cast to `dtype` before use exactly like
+ *               rotation.cu:75 does (`theta.to(x.dtype)`), but inside the kernel
+ *   scales      device [K] of scales_dtype or NULL (rotation.cu:76-78)
+ *   group_size  64 or 128 (rotation.cu:117-123); krot 1..16
+ * Rounding points are those of rotation.cuh:91-173 (fp16/bf16) and :16-75 (fp32).       */
+int paro_rotate(const void *x, void *out, const int16_t *idx_ij, const void *theta,
+                int32_t theta_dtype, const void *scales, int32_t scales_dtype, int64_t M,
+                int32_t K, int32_t krot, int32_t group_size, int32_t dtype, paro_stream_t stream);
+
+/* Size in bytes of the kernel-layout buffer paro_prepack fills (0 on invalid shape). */
+size_t paro_packed_bytes(const paro_linear_shape *shape);
+
+/* One-time repack of checkpoint-format buffers into the streaming layout of the fused kernels.
+ *   qweight  device [K, N/8] int32, AWQ nibble order (convert.py:19,149-155)
+ *   qzeros   device [K/G, N/8] int32
+ *   scales   device [K/G, N] of scales_dtype (fp16 on disk; vLLM holds them in the model dtype)
+ *   pairs    device [n_parts, krot, K] int16
+ *   theta    device [n_parts, krot, K/2] of theta_dtype
+ *   channel_scales device [n_parts, K] of cs_dtype
+ *   packed   device, paro_packed_bytes(shape) bytes, 128-byte aligned
+ * Values are preserved exactly: the kernels reproduce T((q - z) * T(s)) and the reference
+ * rotation bit for bit; only the layout changes.                                         */
+int paro_prepack(const paro_linear_shape *shape, const int32_t *qweight, const int32_t *qzeros,
+                 const void *scales, int32_t scales_dtype, const int16_t *pairs,
+                 const void *theta, int32_t theta_dtype, const void *channel_scales,
+                 int32_t cs_dtype, void *packed, paro_stream_t stream);
+
+/* Bytes of scratch paro_linear_forward needs for up to max_m rows.  The caller zero-fills it
+ * once after allocation; the kernels leave it zeroed again after every launch.          */
+size_t paro_workspace_bytes(const paro_linear_shape *shape, int64_t max_m);
+
+/* y[M, N] = rotate_p(x) . dequant(W)[:, part p] for every partition p (+ bias) in ONE call.
+ *   packed     device buffer from paro_prepack
+ *   x          device [M, K] of shape->dtype, contiguous
+ *   bias       device [N] of shape->dtype or NULL
+ *   y          device [M, N] of shape->dtype
+ *   workspace  device, >= paro_workspace_bytes(shape, M), zeroed before first use
+ * M <= 16 runs the fused rotate+dequant+GEMV kernel (HBM-bound); larger M the
+ * rotate + tcgen05 GEMM path.                                                            */
+int paro_linear_forward(const paro_linear_shape *shape, const void *packed, const void *x,
+                        int64_t M, const void *bias, void *y, void *workspace,
+                        size_t workspace_bytes, paro_stream_t stream);
+
+/* Debug / test aid: dequantise the prepacked weights back to a dense [K, N] matrix of
+ * shape->dtype (the exact operand the GEMM consumes).                                    */
+int paro_unpack_dense(const paro_linear_shape *shape, const void *packed, void *W_out,
+                      paro_stream_t stream);
+
+/* Number of kernels the last successful paro_linear_forward / paro_rotate call on this
+ * thread launched (bench.py's gpu_launches accounting).                                  */
+int paro_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARO_B200_H_ */

@@ -1,0 +1,190 @@
+// One-time AWQ checkpoint layout -> streaming layout (see paro_layout.h), and its inverse for
+// tests.  Integer work, bit-exact by construction; replaces the AWQ->Marlin repack the reference
+// reaches through ParoQuantLinearMethod.process_weights_after_loading
+// (/root/reference/paroquant/inference/backends/vllm/plugin.py:208-279).
+#include "paro_common.cuh"
+#include "paro_layout.h"
+
+namespace paro {
+
+// AWQ: nibble slot i of a word holds column 8c + (0,2,4,6,1,3,5,7)[i]  (cli/convert.py:19)
+__device__ __forceinline__ uint32_t awq_nibble(const int32_t *packed, int64_t row, int n, int ncols8) {
+  const uint32_t w = static_cast<uint32_t>(packed[row * ncols8 + (n >> 3)]);
+  const int c = n & 7;
+  const int slot = (c >> 1) + ((c & 1) << 2);
+  return (w >> (4 * slot)) & 0xFu;
+}
+
+__device__ __forceinline__ uint16_t cast_to_T_bits(const void *p, int64_t i, int src_dtype, int dst_dtype) {
+  float f;
+  if (src_dtype == PARO_F32) f = reinterpret_cast<const float *>(p)[i];
+  else if (src_dtype == PARO_F16) f = __half2float(reinterpret_cast<const __half *>(p)[i]);
+  else f = __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(p)[i]);
+  if (dst_dtype == PARO_F16) return __half_as_ushort(__float2half_rn(f));
+  return __bfloat16_as_ushort(__float2bfloat16_rn(f));
+}
+
+struct PartOffsets {
+  int n_begin[PARO_MAX_PARTS + 1];  // first output column of each partition
+};
+
+__global__ void prepack_meta_kernel(Layout L, const int16_t *__restrict__ pairs, const void *__restrict__ theta,
+                                    int theta_dtype, const void *__restrict__ cscales, int cs_dtype,
+                                    uint8_t *__restrict__ packed) {
+  // one thread per (part, group, channel c in 0..127)
+  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t total = static_cast<int64_t>(L.n_parts) * L.groups * kGroup;
+  if (idx >= total) return;
+  const int c = idx % kGroup;
+  const int gk = (idx / kGroup) % L.groups;
+  const int part = idx / (static_cast<int64_t>(kGroup) * L.groups);
+  uint8_t *blk = packed + L.meta_offset(part, gk);
+  const int K = L.K;
+  for (int r = 0; r < L.krot; ++r) {
+    const int16_t v = pairs[(static_cast<int64_t>(part) * L.krot + r) * K + gk * kGroup + c];
+    blk[r * 128 + c] = static_cast<uint8_t>(v & 0x7F);
+    if (c < 64) {
+      const int64_t ti = (static_cast<int64_t>(part) * L.krot + r) * (K / 2) + gk * 64 + c;
+      reinterpret_cast<uint16_t *>(blk + L.krot * 128)[r * 64 + c] = cast_to_T_bits(theta, ti, theta_dtype, L.dtype);
+    }
+  }
+  reinterpret_cast<uint16_t *>(blk + L.krot * 256)[c] =
+      cast_to_T_bits(cscales, static_cast<int64_t>(part) * K + gk * kGroup + c, cs_dtype, L.dtype);
+}
+
+__global__ void prepack_weight_kernel(Layout L, PartOffsets po, const int32_t *__restrict__ qweight,
+                                      uint8_t *__restrict__ packed) {
+  // one thread per output word: (record, gw, kh, lane, j)
+  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t total = static_cast<int64_t>(L.slices) * L.tiles_total * 1024;
+  if (idx >= total) return;
+  const int j = idx & 3, lane = (idx >> 2) & 31, kh = (idx >> 7) & 1, gw = (idx >> 8) & 3;
+  const int64_t rec = idx >> 10;
+  // record -> (part, slice, tile)
+  int part = 0;
+  while (rec >= static_cast<int64_t>(L.slices) * L.part_tile_begin[part + 1]) ++part;
+  const int tp = L.part_tile_begin[part + 1] - L.part_tile_begin[part];
+  const int64_t rloc = rec - static_cast<int64_t>(L.slices) * L.part_tile_begin[part];
+  const int slice = rloc / tp, tile = rloc % tp;
+  const int g = lane >> 2, t = lane & 3;
+  const int n0 = po.n_begin[part] + tile * kTileN;
+  const int gk = slice * kSliceGroups + gw;
+  uint32_t w = 0;
+  if (gk < L.groups) {
+    const int64_t kb = static_cast<int64_t>(gk) * kGroup + (kh * 4 + j) * 16;
+    const int nc8 = L.N / 8;
+    w |= awq_nibble(qweight, kb + 2 * t, n0 + g, nc8);
+    w |= awq_nibble(qweight, kb + 2 * t, n0 + g + 8, nc8) << 4;
+    w |= awq_nibble(qweight, kb + 2 * t + 8, n0 + g, nc8) << 8;
+    w |= awq_nibble(qweight, kb + 2 * t + 8, n0 + g + 8, nc8) << 12;
+    w |= awq_nibble(qweight, kb + 2 * t + 1, n0 + g, nc8) << 16;
+    w |= awq_nibble(qweight, kb + 2 * t + 1, n0 + g + 8, nc8) << 20;
+    w |= awq_nibble(qweight, kb + 2 * t + 9, n0 + g, nc8) << 24;
+    w |= awq_nibble(qweight, kb + 2 * t + 9, n0 + g + 8, nc8) << 28;
+  }
+  uint32_t *dst = reinterpret_cast<uint32_t *>(packed + L.rec_off + rec * kRecBytes);
+  dst[(gw * 2 + kh) * 128 + lane * 4 + j] = w;
+}
+
+__global__ void prepack_qparam_kernel(Layout L, PartOffsets po, const int32_t *__restrict__ qzeros,
+                                      const void *__restrict__ scales, int scales_dtype,
+                                      uint8_t *__restrict__ packed) {
+  // one thread per (record, gw, g, hi)
+  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t total = static_cast<int64_t>(L.slices) * L.tiles_total * 64;
+  if (idx >= total) return;
+  const int hi = idx & 1, g = (idx >> 1) & 7, gw = (idx >> 4) & 3;
+  const int64_t rec = idx >> 6;
+  int part = 0;
+  while (rec >= static_cast<int64_t>(L.slices) * L.part_tile_begin[part + 1]) ++part;
+  const int tp = L.part_tile_begin[part + 1] - L.part_tile_begin[part];
+  const int64_t rloc = rec - static_cast<int64_t>(L.slices) * L.part_tile_begin[part];
+  const int slice = rloc / tp, tile = rloc % tp;
+  const int n = po.n_begin[part] + tile * kTileN + g + 8 * hi;
+  const int gk = slice * kSliceGroups + gw;
+  uint16_t s = 0;
+  uint8_t z = 0;
+  if (gk < L.groups) {
+    s = cast_to_T_bits(scales, static_cast<int64_t>(gk) * L.N + n, scales_dtype, L.dtype);
+    z = static_cast<uint8_t>(awq_nibble(qzeros, gk, n, L.N / 8));
+  }
+  uint8_t *rb = packed + L.rec_off + rec * kRecBytes;
+  reinterpret_cast<uint16_t *>(rb + kRecScaleOff)[(gw * 8 + g) * 2 + hi] = s;
+  rb[kRecZeroOff + (gw * 8 + g) * 2 + hi] = z;
+}
+
+// Inverse, for tests: dense W[k][n] = T((q - z) * s_T), the exact operand the GEMM consumes.
+template <typename T>
+__global__ void unpack_dense_kernel(Layout L, PartOffsets po, const uint8_t *__restrict__ packed, T *__restrict__ W) {
+  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<int64_t>(L.K) * L.N) return;
+  const int n = idx % L.N;
+  const int k = idx / L.N;
+  int part = 0;
+  while (n >= po.n_begin[part + 1]) ++part;
+  const int nl = n - po.n_begin[part];
+  const int tile = nl / kTileN, g = nl & 7, hi = (nl >> 3) & 1;
+  const int slice = k / kSliceK, gw = (k % kSliceK) / kGroup, kk = (k % kGroup) / 16, kl = k & 15;
+  const int kh = kk >> 2, j = kk & 3;
+  const int k8 = kl >> 3, t = (kl & 7) >> 1, odd = kl & 1;
+  const int lane = g * 4 + t;
+  const uint8_t *rb = packed + L.record_offset(part, slice, tile);
+  const uint32_t w = reinterpret_cast<const uint32_t *>(rb)[(gw * 2 + kh) * 128 + lane * 4 + j];
+  const int q = (w >> (k8 * 8 + hi * 4 + odd * 16)) & 0xF;
+  const int z = rb[kRecZeroOff + (gw * 8 + g) * 2 + hi];
+  const T s = reinterpret_cast<const T *>(rb + kRecScaleOff)[(gw * 8 + g) * 2 + hi];
+  // (q - z) is exact in T; one rounding in the product, like the fused kernels
+  W[idx] = Traits<T>::from_float(static_cast<float>(q - z) * Traits<T>::to_float(s));
+}
+
+static PartOffsets part_offsets(const paro_linear_shape &s) {
+  PartOffsets po;
+  int n = 0;
+  for (int p = 0; p <= PARO_MAX_PARTS; ++p) {
+    po.n_begin[p] = n;
+    if (p < s.n_parts) n += s.part_sizes[p];
+  }
+  return po;
+}
+
+int prepack_launch(const paro_linear_shape &s, const Layout &L, const int32_t *qweight, const int32_t *qzeros,
+                   const void *scales, int scales_dtype, const int16_t *pairs, const void *theta, int theta_dtype,
+                   const void *cscales, int cs_dtype, void *packed, cudaStream_t stream) {
+  const PartOffsets po = part_offsets(s);
+  uint8_t *out = static_cast<uint8_t *>(packed);
+  const int B = 256;
+  {
+    const int64_t total = static_cast<int64_t>(L.n_parts) * L.groups * kGroup;
+    prepack_meta_kernel<<<static_cast<unsigned>((total + B - 1) / B), B, 0, stream>>>(L, pairs, theta, theta_dtype,
+                                                                                     cscales, cs_dtype, out);
+  }
+  {
+    const int64_t total = static_cast<int64_t>(L.slices) * L.tiles_total * 1024;
+    prepack_weight_kernel<<<static_cast<unsigned>((total + B - 1) / B), B, 0, stream>>>(L, po, qweight, out);
+  }
+  {
+    const int64_t total = static_cast<int64_t>(L.slices) * L.tiles_total * 64;
+    prepack_qparam_kernel<<<static_cast<unsigned>((total + B - 1) / B), B, 0, stream>>>(L, po, qzeros, scales,
+                                                                                        scales_dtype, out);
+  }
+  PARO_CUDA_OK(cudaGetLastError());
+  note_launches(3);
+  return PARO_OK;
+}
+
+int unpack_dense_launch(const paro_linear_shape &s, const Layout &L, const void *packed, void *W, cudaStream_t stream) {
+  const PartOffsets po = part_offsets(s);
+  const int64_t total = static_cast<int64_t>(L.K) * L.N;
+  const int B = 256;
+  const unsigned grid = static_cast<unsigned>((total + B - 1) / B);
+  if (L.dtype == PARO_F16)
+    unpack_dense_kernel<__half><<<grid, B, 0, stream>>>(L, po, static_cast<const uint8_t *>(packed), static_cast<__half *>(W));
+  else
+    unpack_dense_kernel<__nv_bfloat16><<<grid, B, 0, stream>>>(L, po, static_cast<const uint8_t *>(packed),
+                                                               static_cast<__nv_bfloat16 *>(W));
+  PARO_CUDA_OK(cudaGetLastError());
+  note_launches(1);
+  return PARO_OK;
+}
+
+}  // namespace paro

@@ -1,0 +1,240 @@
+// Standalone scaled pairwise (Givens) rotation for sm_100a -- the torch.ops.rotation.rotate
+// surface (/root/reference/paroquant/kernels/cuda/rotation.cu:10-43,62-135) and the
+// activation pre-pass of the large-M GEMM path.
+//
+// Arithmetic is the reference's, rounding point for rounding point (rotation.cuh:91-173 for
+// fp16/bf16, :16-75 for fp32): v = T(x * T(scale)); per rotation r and pair (i, j):
+// (s, c) = __sincosf(float(T(theta))), vi' = T(fma(c, vi, s*vj)), vj' = T(fma(c, vj, s*-vi)).
+//
+// Mapping (not the reference's): one WARP owns one (block of RB rows, group) tile, so the
+// krot rotations need only __syncwarp().  The tile lives in shared memory channel-major --
+// rot[channel][RB rows] = one 16-byte vector per channel -- so a pair update is two 128-bit
+// loads and two 128-bit stores for all RB rows at once.  The 16-byte slot of channel c is
+// c ^ ((c >> 3) & 7), which makes the coalesced transpose-in / transpose-out conflict free.
+#include "paro_common.cuh"
+
+namespace paro {
+
+template <typename T> struct RotVec;  // 16-byte vector of RB rows of one channel
+
+template <> struct RotVec<float> {
+  static constexpr int RB = 4;
+};
+template <> struct RotVec<__half> {
+  static constexpr int RB = 8;
+};
+template <> struct RotVec<__nv_bfloat16> {
+  static constexpr int RB = 8;
+};
+
+__device__ __forceinline__ int rot_slot(int c) { return c ^ ((c >> 3) & 7); }
+
+// ---- half / bf16: a channel vector is 4 x T2 words, word u = rows (2u, 2u+1)
+template <typename T>
+__device__ __forceinline__ void pair_update(uint4 &vi, uint4 &vj, float c, float s) {
+  uint32_t *pi = reinterpret_cast<uint32_t *>(&vi), *pj = reinterpret_cast<uint32_t *>(&vj);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const float2 a = Traits<T>::to_float2(unpack2<T>(pi[u]));
+    const float2 b = Traits<T>::to_float2(unpack2<T>(pj[u]));
+    float yix, yiy, yjx, yjy;
+    givens(c, s, a.x, b.x, yix, yjx);
+    givens(c, s, a.y, b.y, yiy, yjy);
+    pi[u] = pack2<T>(Traits<T>::from_floats(yix, yiy));
+    pj[u] = pack2<T>(Traits<T>::from_floats(yjx, yjy));
+  }
+}
+template <>
+__device__ __forceinline__ void pair_update<float>(uint4 &vi, uint4 &vj, float c, float s) {
+  float *pi = reinterpret_cast<float *>(&vi), *pj = reinterpret_cast<float *>(&vj);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    float yi, yj;
+    givens(c, s, pi[u], pj[u], yi, yj);
+    pi[u] = yi;
+    pj[u] = yj;
+  }
+}
+
+template <typename T, int G>
+__global__ void __launch_bounds__(128) rotate_kernel(const T *__restrict__ x, T *__restrict__ out,
+                                                     const int16_t *__restrict__ idx, const void *__restrict__ theta,
+                                                     int theta_dtype, const void *__restrict__ scales, int scales_dtype,
+                                                     int64_t M, int K, int krot) {
+  constexpr int RB = RotVec<T>::RB;
+  constexpr int CPL = G / 32;  // channels per lane for the coalesced load / store
+  constexpr int PPL = G / 64;  // pairs per lane
+  __shared__ __align__(16) uint4 tile[4][G];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int groups = K / G;
+  const int64_t task = static_cast<int64_t>(blockIdx.x) * 4 + warp;
+  const int64_t row_blocks = (M + RB - 1) / RB;
+  if (task >= row_blocks * groups) return;
+  const int g = static_cast<int>(task % groups);
+  const int64_t row0 = (task / groups) * RB;
+  uint4 *rot = tile[warp];
+
+  // ---- load RB rows x CPL channels per lane, scale, transpose into rot[channel]
+  {
+    float sc[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c)
+      sc[c] = scales ? load_param_as<T>(scales, static_cast<int64_t>(g) * G + lane * CPL + c, scales_dtype) : 1.0f;
+    if constexpr (sizeof(T) == 4) {
+      float v[RB][CPL];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const bool ok = row0 + r < M;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+          const float xv = ok ? x[(row0 + r) * K + g * G + lane * CPL + c] : 0.0f;
+          v[r][c] = scales ? xv * sc[c] : xv;  // rotation.cuh:24-32
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        uint4 w;
+        float *pw = reinterpret_cast<float *>(&w);
+#pragma unroll
+        for (int r = 0; r < RB; ++r) pw[r] = v[r][c];
+        rot[rot_slot(lane * CPL + c)] = w;
+      }
+    } else {
+      T v[RB][CPL];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const bool ok = row0 + r < M;
+        if constexpr (CPL == 4) {
+          uint2 raw = ok ? *reinterpret_cast<const uint2 *>(x + (row0 + r) * K + g * G + lane * 4) : make_uint2(0, 0);
+          const T *pr = reinterpret_cast<const T *>(&raw);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) v[r][c] = pr[c];
+        } else {
+          uint32_t raw = ok ? *reinterpret_cast<const uint32_t *>(x + (row0 + r) * K + g * G + lane * 2) : 0u;
+          const T *pr = reinterpret_cast<const T *>(&raw);
+          v[r][0] = pr[0];
+          v[r][1] = pr[1];
+        }
+        if (scales) {
+#pragma unroll
+          for (int c = 0; c < CPL; ++c) v[r][c] = __hmul(v[r][c], Traits<T>::from_float(sc[c]));  // one rounding, cuh:112-113
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        uint4 w;
+        T *pw = reinterpret_cast<T *>(&w);
+#pragma unroll
+        for (int r = 0; r < RB; ++r) pw[r] = v[r][c];
+        rot[rot_slot(lane * CPL + c)] = w;
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---- krot rotations; lane owns pairs lane*PPL .. lane*PPL+PPL-1 of each rotation
+  for (int r = 0; r < krot; ++r) {
+    int pi[PPL], pj[PPL];
+    float cs[PPL], sn[PPL];
+#pragma unroll
+    for (int q = 0; q < PPL; ++q) {
+      const int t = lane * PPL + q;
+      const int ij = *reinterpret_cast<const int *>(idx + static_cast<int64_t>(r) * K + g * G + 2 * t);
+      pi[q] = ij & 0xFFFF;
+      pj[q] = (ij >> 16) & 0xFFFF;
+      const float th = load_param_as<T>(theta, static_cast<int64_t>(r) * (K / 2) + g * (G / 2) + t, theta_dtype);
+      __sincosf(th, &sn[q], &cs[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < PPL; ++q) {
+      uint4 vi = rot[rot_slot(pi[q])], vj = rot[rot_slot(pj[q])];
+      pair_update<T>(vi, vj, cs[q], sn[q]);
+      rot[rot_slot(pi[q])] = vi;
+      rot[rot_slot(pj[q])] = vj;
+    }
+    __syncwarp();
+  }
+
+  // ---- transpose out
+  if constexpr (sizeof(T) == 4) {
+    float v[RB][CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const uint4 w = rot[rot_slot(lane * CPL + c)];
+      const float *pw = reinterpret_cast<const float *>(&w);
+#pragma unroll
+      for (int r = 0; r < RB; ++r) v[r][c] = pw[r];
+    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r)
+      if (row0 + r < M) {
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) out[(row0 + r) * K + g * G + lane * CPL + c] = v[r][c];
+      }
+  } else {
+    T v[RB][CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const uint4 w = rot[rot_slot(lane * CPL + c)];
+      const T *pw = reinterpret_cast<const T *>(&w);
+#pragma unroll
+      for (int r = 0; r < RB; ++r) v[r][c] = pw[r];
+    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r)
+      if (row0 + r < M) {
+        if constexpr (CPL == 4) {
+          uint2 raw;
+          T *pr = reinterpret_cast<T *>(&raw);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) pr[c] = v[r][c];
+          *reinterpret_cast<uint2 *>(out + (row0 + r) * K + g * G + lane * 4) = raw;
+        } else {
+          uint32_t raw;
+          T *pr = reinterpret_cast<T *>(&raw);
+          pr[0] = v[r][0];
+          pr[1] = v[r][1];
+          *reinterpret_cast<uint32_t *>(out + (row0 + r) * K + g * G + lane * 2) = raw;
+        }
+      }
+  }
+}
+
+template <typename T>
+static int launch_T(const void *x, void *out, const int16_t *idx, const void *theta, int theta_dtype,
+                    const void *scales, int scales_dtype, int64_t M, int K, int krot, int G, cudaStream_t stream) {
+  constexpr int RB = RotVec<T>::RB;
+  const int64_t tasks = ((M + RB - 1) / RB) * (K / G);
+  const int64_t blocks = (tasks + 3) / 4;
+  if (blocks > 0x7FFFFFFF) {
+    set_error("rotate: too many rows");
+    return PARO_EINVAL;
+  }
+  const T *xp = static_cast<const T *>(x);
+  T *op = static_cast<T *>(out);
+  if (G == 128)
+    rotate_kernel<T, 128><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(xp, op, idx, theta, theta_dtype, scales,
+                                                                            scales_dtype, M, K, krot);
+  else
+    rotate_kernel<T, 64><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(xp, op, idx, theta, theta_dtype, scales,
+                                                                           scales_dtype, M, K, krot);
+  PARO_CUDA_OK(cudaGetLastError());
+  note_launches(1);
+  return PARO_OK;
+}
+
+int rotate_launch(const void *x, void *out, const int16_t *idx, const void *theta, int theta_dtype, const void *scales,
+                  int scales_dtype, int64_t M, int K, int krot, int G, int dtype, cudaStream_t stream) {
+  if (M == 0) return PARO_OK;
+  switch (dtype) {
+    case PARO_F32: return launch_T<float>(x, out, idx, theta, theta_dtype, scales, scales_dtype, M, K, krot, G, stream);
+    case PARO_F16: return launch_T<__half>(x, out, idx, theta, theta_dtype, scales, scales_dtype, M, K, krot, G, stream);
+    case PARO_BF16:
+      return launch_T<__nv_bfloat16>(x, out, idx, theta, theta_dtype, scales, scales_dtype, M, K, krot, G, stream);
+  }
+  set_error("rotate supports Float, Half, and BFloat16, got dtype code %d", dtype);
+  return PARO_EINVAL;
+}
+
+}  // namespace paro

@@ -1,0 +1,79 @@
+"""The C-ABI boundary without a GPU: the library loads, exports every symbol include/*.h
+declares, and its host-side checks / size queries behave (no compute calls here)."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+from paroquant_b200 import _cabi
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _declared_symbols():
+    text = (ROOT / "include" / "paro_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(paro_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _cabi.lib()
+    names = _declared_symbols()
+    assert len(names) >= 9
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/paro_b200.h but not exported"
+    assert set(names) == set(_cabi.EXPORTED_SYMBOLS)
+    assert lib.paro_abi_version() == 1
+
+
+def test_struct_layout_matches_header():
+    assert ctypes.sizeof(_cabi.ParoLinearShape) == 4 * (5 + 8 + 1)
+
+
+def test_size_queries_and_shape_errors():
+    s = _cabi.make_shape(4096, [4096], 128, 8, torch.bfloat16)
+    # 8 slices x 256 tiles x 4288-byte records + 32 groups x (8*256+256) bytes of rotation metadata
+    assert _cabi.packed_bytes(s) == 8 * 256 * 4288 + 32 * 2304
+    assert _cabi.workspace_bytes(s, 1) >= 256 * 4 + 8 * 256 * 512
+    assert _cabi.workspace_bytes(s, 16) >= _cabi.workspace_bytes(s, 8)
+    for bad, msg in ((dict(in_features=4000), "multiple of 128"), (dict(part_sizes=[100]), "multiple of 16"),
+                     (dict(group_size=64), "group_size"), (dict(krot=17), "krot")):
+        kw = dict(in_features=4096, part_sizes=[4096], group_size=128, krot=8, dtype=torch.bfloat16)
+        kw.update(bad)
+        with pytest.raises(RuntimeError, match=msg):
+            _cabi.packed_bytes(_cabi.make_shape(**kw))
+    with pytest.raises(RuntimeError, match="Float, Half, and BFloat16"):
+        _cabi.make_shape(4096, [4096], 128, 8, torch.int8)
+
+
+def test_merged_layout_is_partition_major():
+    s = _cabi.make_shape(4096, [4096, 1024, 1024], 128, 8, torch.float16)
+    assert _cabi.packed_bytes(s) == 8 * 384 * 4288 + ((3 * 32 * 2304 + 127) // 128) * 128
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    x = torch.zeros(2, 128)
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        _cabi.rotate(x, torch.zeros(8, 128, dtype=torch.int16), torch.zeros(8, 64))
+    import paroquant_b200.kernels.cuda  # noqa: F401
+    with pytest.raises(NotImplementedError):
+        torch.ops.rotation.rotate(x, torch.zeros(8, 128, dtype=torch.int16), torch.zeros(8, 64))
+
+
+def test_null_and_bad_arguments_return_codes():
+    lib = _cabi.lib()
+    rc = lib.paro_rotate(None, None, None, None, 0, None, 0, 1, 128, 8, 128, 2, None)
+    assert rc == 1 and b"null pointer" in lib.paro_last_error()
+    buf = (ctypes.c_char * 4096)()
+    p = ctypes.addressof(buf)
+    p = (p + 255) // 256 * 256
+    rc = lib.paro_rotate(p, p, p, p, 1, None, 0, 1, 128, 8, 32, 2, None)
+    assert rc == 2 and b"Unsupported group_size: 32; expected 64 or 128" in lib.paro_last_error()
+    rc = lib.paro_rotate(p, p, p, p, 1, None, 0, 1, 100, 8, 64, 2, None)
+    assert rc == 1 and b"h must be divisible by GROUP_SIZE" in lib.paro_last_error()
+    rc = lib.paro_rotate(p, p, p, p, 1, None, 0, 1, 128, 8, 128, 7, None)
+    assert rc == 1 and b"Float, Half, and BFloat16" in lib.paro_last_error()
+    rc = lib.paro_rotate(p, p, p, p, 1, None, 0, 0, 128, 8, 128, 2, None)   # empty input: no launch, success
+    assert rc == 0 and lib.paro_last_launch_count() == 0
