@@ -42,6 +42,7 @@ struct DecodeParams {
   int *counters;
   int M, K, N;
   int n_parts, slices, groups, krot, nstages, tiles_total;
+  int rot_bytes;  // per consumer warp: 128 channels x (padded rows) x sizeof(T)
   int part_tile_begin[PARO_MAX_PARTS + 1];
   int part_cta_begin[PARO_MAX_PARTS + 1];
   int meta_group_bytes;
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(kDecodeThreads, (MB == 1 ? 3 : 2)) decode_kern
   const int nst = p.nstages;
   uint8_t *stage_base = smem;
   const uint32_t rot_all = smem_u32(smem + static_cast<size_t>(nst) * kStageBytes);
-  constexpr int kRotBytesPerWarp = kGroup * 16 * MB;  // up to 8*MB rows of T per channel
+  const int kRotBytesPerWarp = p.rot_bytes;
   const uint32_t bars = rot_all + 4 * kRotBytesPerWarp;
   const uint32_t bar_full = bars, bar_empty = bars + 8 * kMaxStages, bar_part = bars + 16 * kMaxStages;
 
@@ -504,7 +505,7 @@ static int env_int(const char *name, int dflt) {
 
 template <typename T, int MB, int KROT>
 static int launch_decode(const DecodeParams &p, const DecodePlan &plan, cudaStream_t stream) {
-  const size_t smem = static_cast<size_t>(p.nstages) * kStageBytes + 4 * (kGroup * 16 * MB) + 3 * 8 * kMaxStages;
+  const size_t smem = static_cast<size_t>(p.nstages) * kStageBytes + 4 * p.rot_bytes + 3 * 8 * kMaxStages;
   auto kern = decode_kernel<T, MB, KROT>;
   PARO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   cudaLaunchConfig_t cfg = {};
@@ -550,6 +551,7 @@ int decode_forward(const paro_linear_shape &s, const Layout &L, const void *pack
   if (nst < 1) nst = 1;
   if (nst > kMaxStages) nst = kMaxStages;
   p.nstages = nst;
+  p.rot_bytes = kGroup * 2 * (M <= 2 ? 2 : M <= 4 ? 4 : M <= 8 ? 8 : 16);
   for (int i = 0; i <= PARO_MAX_PARTS; ++i) {
     p.part_tile_begin[i] = L.part_tile_begin[i];
     p.part_cta_begin[i] = plan.part_cta_begin[i];

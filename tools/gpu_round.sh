@@ -1,0 +1,25 @@
+#!/bin/bash
+# One gpurun call: smoke -> GPU tests -> reference fixtures -> bench -> microbench -> ncu launch list.
+# Every step has its own timeout; later steps run even if earlier ones fail.  Logs in gpurun_out/.
+set +e
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/gpu.csv 2>&1
+echo "== smoke"; timeout -s KILL 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/smoke.log
+if [ "${SKIP_TESTS:-0}" != "1" ]; then
+echo "== pytest gpu"; timeout -s KILL 1500 python -m pytest tests -m gpu -q --timeout 300 --timeout-method=thread -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -25 gpurun_out/pytest_gpu.log
+fi
+if [ "${GOLDEN:-0}" = "1" ]; then
+echo "== golden"; timeout -s KILL 900 python tools/ref_gpu.py golden gpurun_out/golden > gpurun_out/golden.log 2>&1; echo "golden rc=$?"; tail -3 gpurun_out/golden.log
+fi
+echo "== bench"; timeout -s KILL 900 python bench.py --steps ${STEPS:-200} --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+if [ "${MICRO:-1}" = "1" ]; then
+echo "== microbench"; timeout -s KILL 900 python tools/microbench.py --out gpurun_out/micro.json ${MICRO_ARGS:-} > gpurun_out/micro.log 2>&1; echo "micro rc=$?"; cat gpurun_out/micro.log | tail -20
+fi
+if [ "${NCU:-0}" = "1" ]; then
+echo "== ncu launch list"; timeout -s KILL 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 300 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-graph --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo "ncu rc=$?"
+echo "== ncu full"; timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:decode_kernel -s 140 -c 4 -o gpurun_out/prof_decode python bench.py --steps 1 --warmup 1 --no-graph --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
+fi
+if [ "${REFBENCH:-0}" = "1" ]; then
+echo "== reference GPU path"; timeout -s KILL 1200 python tools/ref_gpu.py bench gpurun_out/ref_gpu_bench.json --m 1 > gpurun_out/ref_gpu_bench.log 2>&1; echo "refbench rc=$?"; tail -2 gpurun_out/ref_gpu_bench.log
+fi
+echo "== done"
