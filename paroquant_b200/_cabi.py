@@ -131,6 +131,9 @@ def rotate(x: torch.Tensor, idx_ij: torch.Tensor, theta: torch.Tensor, scales: t
     out = torch.empty_like(x)
     K = x.size(-1)
     M = x.numel() // K if K else 0
+    if M == 0:
+        dtype_code(x.dtype)
+        return out
     with torch.cuda.device(dev):
         rc = lib().paro_rotate(x.data_ptr(), out.data_ptr(), idx_ij.data_ptr(), theta.data_ptr(), dtype_code(theta.dtype),
                                scales.data_ptr() if has_scale else None, dtype_code(scales.dtype) if has_scale else 0,
@@ -190,6 +193,8 @@ def linear_forward(shape: ParoLinearShape, packed: torch.Tensor, x: torch.Tensor
         out = torch.empty(*x.shape[:-1], shape.out_features, dtype=x.dtype, device=dev)
     if bias is not None:
         bias = bias.to(x.dtype).contiguous()
+    if M == 0:
+        return out
     need = workspace_bytes(shape, M)
     if workspace.numel() < need:
         raise RuntimeError(f"linear_forward: workspace has {workspace.numel()} bytes, {need} needed for M={M}")

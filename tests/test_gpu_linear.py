@@ -82,9 +82,9 @@ def test_llama_shapes_vs_oracle_and_dense(PK, oracle, K, parts):
             xr = torch.ops.rotation.rotate(x, L.pairs[p], L.theta[p], L.channel_scales[p]).float()
             chunks.append(xr.double() @ W[:, n0:n0 + n].double())
             n0 += n
-        ref = torch.cat(chunks, -1)
+        ref = torch.cat(chunks, -1).float().to(torch.bfloat16).double()   # same single final rounding
         err = ((y.double() - ref).norm() / ref.norm()).item()
-        assert err < TOL, (M, err)
+        assert err < 3e-4, (M, err)                                        # only rare one-ulp flips remain
     # oracle on a column sample (full oracle GEMM at these sizes would take minutes)
     cols = torch.arange(0, sum(parts), max(1, sum(parts) // 257))[:256]
     d = L.to("cpu").numpy_dict()
@@ -110,8 +110,8 @@ def test_properties_at_full_size(PK):
     W = k.dense_weight().double()
     x = make_synthetic_activations(16, 4096, seed=9, device="cuda")
     y = k(x)
-    ref = x.double() @ W
-    assert ((y.double() - ref).norm() / ref.norm()).item() < 2e-3 * 0.5   # only the final rounding to bf16 differs
+    ref = (x.double() @ W).float().to(torch.bfloat16).double()
+    assert ((y.double() - ref).norm() / ref.norm()).item() < 3e-4           # identical up to rare one-ulp flips
     assert torch.equal(k(x * 4), y * 4)
     for m in (0, 7, 15):
         assert torch.equal(k(x[m:m + 1]), y[m:m + 1])
