@@ -54,12 +54,13 @@ __global__ void prepack_meta_kernel(Layout L, const int16_t *__restrict__ pairs,
 
 __global__ void prepack_weight_kernel(Layout L, PartOffsets po, const int32_t *__restrict__ qweight,
                                       uint8_t *__restrict__ packed) {
-  // one thread per output word: (record, gw, kh, lane, j)
+  // one thread per output word: (record, unit u, kh, lane, j)
   const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  const int64_t total = static_cast<int64_t>(L.slices) * L.tiles_total * 1024;
+  const int64_t total = static_cast<int64_t>(L.slices) * L.tiles_total * L.gps * 256;
   if (idx >= total) return;
-  const int j = idx & 3, lane = (idx >> 2) & 31, kh = (idx >> 7) & 1, gw = (idx >> 8) & 3;
-  const int64_t rec = idx >> 10;
+  const int j = idx & 3, lane = (idx >> 2) & 31, kh = (idx >> 7) & 1;
+  const int u = static_cast<int>((idx >> 8) % L.gps);
+  const int64_t rec = idx / (256 * static_cast<int64_t>(L.gps));
   // record -> (part, slice, tile)
   int part = 0;
   while (rec >= static_cast<int64_t>(L.slices) * L.part_tile_begin[part + 1]) ++part;
@@ -68,7 +69,7 @@ __global__ void prepack_weight_kernel(Layout L, PartOffsets po, const int32_t *_
   const int slice = rloc / tp, tile = rloc % tp;
   const int g = lane >> 2, t = lane & 3;
   const int n0 = po.n_begin[part] + tile * kTileN;
-  const int gk = slice * kSliceGroups + gw;
+  const int gk = slice * L.gps + u;
   uint32_t w = 0;
   if (gk < L.groups) {
     const int64_t kb = static_cast<int64_t>(gk) * kGroup + (kh * 4 + j) * 16;
@@ -82,35 +83,36 @@ __global__ void prepack_weight_kernel(Layout L, PartOffsets po, const int32_t *_
     w |= awq_nibble(qweight, kb + 2 * t + 9, n0 + g, nc8) << 24;
     w |= awq_nibble(qweight, kb + 2 * t + 9, n0 + g + 8, nc8) << 28;
   }
-  uint32_t *dst = reinterpret_cast<uint32_t *>(packed + L.rec_off + rec * kRecBytes);
-  dst[(gw * 2 + kh) * 128 + lane * 4 + j] = w;
+  uint32_t *dst = reinterpret_cast<uint32_t *>(packed + L.rec_off + rec * L.rec_bytes);
+  dst[(u * 2 + kh) * 128 + lane * 4 + j] = w;
 }
 
 __global__ void prepack_qparam_kernel(Layout L, PartOffsets po, const int32_t *__restrict__ qzeros,
                                       const void *__restrict__ scales, int scales_dtype,
                                       uint8_t *__restrict__ packed) {
-  // one thread per (record, gw, g, hi)
+  // one thread per (record, unit u, g, hi)
   const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  const int64_t total = static_cast<int64_t>(L.slices) * L.tiles_total * 64;
+  const int64_t total = static_cast<int64_t>(L.slices) * L.tiles_total * L.gps * 16;
   if (idx >= total) return;
-  const int hi = idx & 1, g = (idx >> 1) & 7, gw = (idx >> 4) & 3;
-  const int64_t rec = idx >> 6;
+  const int hi = idx & 1, g = (idx >> 1) & 7;
+  const int u = static_cast<int>((idx >> 4) % L.gps);
+  const int64_t rec = idx / (16 * static_cast<int64_t>(L.gps));
   int part = 0;
   while (rec >= static_cast<int64_t>(L.slices) * L.part_tile_begin[part + 1]) ++part;
   const int tp = L.part_tile_begin[part + 1] - L.part_tile_begin[part];
   const int64_t rloc = rec - static_cast<int64_t>(L.slices) * L.part_tile_begin[part];
   const int slice = rloc / tp, tile = rloc % tp;
   const int n = po.n_begin[part] + tile * kTileN + g + 8 * hi;
-  const int gk = slice * kSliceGroups + gw;
+  const int gk = slice * L.gps + u;
   uint16_t s = 0;
   uint8_t z = 0;
   if (gk < L.groups) {
     s = cast_to_T_bits(scales, static_cast<int64_t>(gk) * L.N + n, scales_dtype, L.dtype);
     z = static_cast<uint8_t>(awq_nibble(qzeros, gk, n, L.N / 8));
   }
-  uint8_t *rb = packed + L.rec_off + rec * kRecBytes;
-  reinterpret_cast<uint16_t *>(rb + kRecScaleOff)[(gw * 8 + g) * 2 + hi] = s;
-  rb[kRecZeroOff + (gw * 8 + g) * 2 + hi] = z;
+  uint8_t *rb = packed + L.rec_off + rec * L.rec_bytes;
+  reinterpret_cast<uint16_t *>(rb + L.gps * kUnitWeightBytes)[(u * 8 + g) * 2 + hi] = s;
+  rb[L.gps * (kUnitWeightBytes + 32) + (u * 8 + g) * 2 + hi] = z;
 }
 
 // Inverse, for tests: dense W[k][n] = T((q - z) * s_T), the exact operand the GEMM consumes.
@@ -124,15 +126,15 @@ __global__ void unpack_dense_kernel(Layout L, PartOffsets po, const uint8_t *__r
   while (n >= po.n_begin[part + 1]) ++part;
   const int nl = n - po.n_begin[part];
   const int tile = nl / kTileN, g = nl & 7, hi = (nl >> 3) & 1;
-  const int slice = k / kSliceK, gw = (k % kSliceK) / kGroup, kk = (k % kGroup) / 16, kl = k & 15;
+  const int gk = k / kGroup, slice = gk / L.gps, gw = gk % L.gps, kk = (k % kGroup) / 16, kl = k & 15;
   const int kh = kk >> 2, j = kk & 3;
   const int k8 = kl >> 3, t = (kl & 7) >> 1, odd = kl & 1;
   const int lane = g * 4 + t;
   const uint8_t *rb = packed + L.record_offset(part, slice, tile);
   const uint32_t w = reinterpret_cast<const uint32_t *>(rb)[(gw * 2 + kh) * 128 + lane * 4 + j];
   const int q = (w >> (k8 * 8 + hi * 4 + odd * 16)) & 0xF;
-  const int z = rb[kRecZeroOff + (gw * 8 + g) * 2 + hi];
-  const T s = reinterpret_cast<const T *>(rb + kRecScaleOff)[(gw * 8 + g) * 2 + hi];
+  const int z = rb[L.gps * (kUnitWeightBytes + 32) + (gw * 8 + g) * 2 + hi];
+  const T s = reinterpret_cast<const T *>(rb + L.gps * kUnitWeightBytes)[(gw * 8 + g) * 2 + hi];
   // (q - z) is exact in T; one rounding in the product, like the fused kernels
   W[idx] = Traits<T>::from_float(static_cast<float>(q - z) * Traits<T>::to_float(s));
 }
@@ -159,11 +161,11 @@ int prepack_launch(const paro_linear_shape &s, const Layout &L, const int32_t *q
                                                                                      cscales, cs_dtype, out);
   }
   {
-    const int64_t total = static_cast<int64_t>(L.slices) * L.tiles_total * 1024;
+    const int64_t total = static_cast<int64_t>(L.slices) * L.tiles_total * L.gps * 256;
     prepack_weight_kernel<<<static_cast<unsigned>((total + B - 1) / B), B, 0, stream>>>(L, po, qweight, out);
   }
   {
-    const int64_t total = static_cast<int64_t>(L.slices) * L.tiles_total * 64;
+    const int64_t total = static_cast<int64_t>(L.slices) * L.tiles_total * L.gps * 16;
     prepack_qparam_kernel<<<static_cast<unsigned>((total + B - 1) / B), B, 0, stream>>>(L, po, qzeros, scales,
                                                                                         scales_dtype, out);
   }
