@@ -125,6 +125,11 @@ int paro_unpack_dense(const paro_linear_shape *shape, const void *packed, void *
  * thread launched (bench.py's gpu_launches accounting).                                  */
 int paro_last_launch_count(void);
 
+/* Developer aid: with PARO_DECODE_TRACE=1 in the environment the small-M kernel records, per CTA,
+ * 12 uint64 values (phase timestamps in SM cycles relative to kernel entry, %globaltimer at entry
+ * and exit).  Copies the first max_ctas x 12 values of the last launch to host_out (synchronous). */
+int paro_debug_trace(unsigned long long *host_out, int32_t max_ctas);
+
 #ifdef __cplusplus
 }
 #endif

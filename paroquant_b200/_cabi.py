@@ -61,6 +61,8 @@ def lib() -> ctypes.CDLL:
         L.paro_linear_forward.argtypes = [shp, vp, vp, i64, vp, vp, vp, sz, vp]
         L.paro_unpack_dense.restype = ctypes.c_int
         L.paro_unpack_dense.argtypes = [shp, vp, vp, vp]
+        L.paro_debug_trace.restype = ctypes.c_int
+        L.paro_debug_trace.argtypes = [vp, i32]
         if L.paro_abi_version() != 1:
             raise ImportError("libparo_b200.so ABI version mismatch")
         _lib = L
@@ -69,7 +71,7 @@ def lib() -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = (
     "paro_abi_version", "paro_last_error", "paro_last_launch_count", "paro_rotate", "paro_packed_bytes",
-    "paro_prepack", "paro_workspace_bytes", "paro_linear_forward", "paro_unpack_dense",
+    "paro_prepack", "paro_workspace_bytes", "paro_linear_forward", "paro_unpack_dense", "paro_debug_trace",
 )
 
 

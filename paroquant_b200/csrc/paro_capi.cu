@@ -32,6 +32,7 @@ size_t decode_workspace_bytes(const Layout &L, int64_t max_m);
 int decode_forward(const paro_linear_shape &s, const Layout &L, const void *packed, const void *x, int64_t M,
                    const void *bias, void *y, void *workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t gemm_workspace_bytes(const Layout &L, int64_t max_m);
+int debug_trace_read(unsigned long long *host, int max_ctas);
 int gemm_forward(const paro_linear_shape &s, const Layout &L, const void *packed, const void *x, int64_t M,
                  const void *bias, void *y, void *workspace, size_t workspace_bytes, cudaStream_t stream);
 
@@ -122,6 +123,11 @@ int paro_unpack_dense(const paro_linear_shape *shape, const void *packed, void *
   if (!shape || !make_layout(*shape, L, &why)) { set_error("unpack_dense: %s", shape ? why : "null shape"); return PARO_EINVAL; }
   if (!packed || !W_out) { set_error("unpack_dense: null pointer argument"); return PARO_EINVAL; }
   return unpack_dense_launch(*shape, L, packed, W_out, static_cast<cudaStream_t>(stream));
+}
+
+int paro_debug_trace(unsigned long long *host_out, int32_t max_ctas) {
+  if (!host_out || max_ctas <= 0) { set_error("debug_trace: bad arguments"); return PARO_EINVAL; }
+  return debug_trace_read(host_out, max_ctas);
 }
 
 }  // extern "C"

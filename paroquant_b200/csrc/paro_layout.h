@@ -10,17 +10,17 @@
 //
 // Weight records.  K is cut into `slices` of `gps` groups (gps*128 channels; the plan below picks
 // gps from K so that one slice is what ONE CTA of the small-M kernel owns), N into tiles of 16
-// columns.  One record = one (slice, tile) = 16 x gps*128 INT4 weights + their scales / zeros:
-//   [u = 0..gps-1][kh = 0..1][lane = 0..31] 16 bytes = 4 words, word j covers the 16 k values
-//        kb = (slice*gps + u)*128 + (kh*4 + j)*16 .. +15  for the two columns n0+g, n0+g+8
-//        (g = lane/4, t = lane%4) in exactly the register layout of the A operand of
-//        mma.m16n8k16 (rows = output columns n, cols = k):
-//          bits  0..3   W[kb+2t  ][n0+g]      bits 16..19  W[kb+2t+1][n0+g]
-//          bits  4..7   W[kb+2t  ][n0+g+8]    bits 20..23  W[kb+2t+1][n0+g+8]
-//          bits  8..11  W[kb+2t+8][n0+g]      bits 24..27  W[kb+2t+9][n0+g]
-//          bits 12..15  W[kb+2t+8][n0+g+8]    bits 28..31  W[kb+2t+9][n0+g+8]
-//   [u][g = 0..7][2] T      scales  s[slice*gps+u][n0+g], s[..][n0+g+8]            (gps*32 bytes)
-//   [u][g = 0..7][2] uint8  zeros   z[slice*gps+u][n0+g], z[..][n0+g+8]            (gps*16 bytes)
+// output columns.  One record = one (slice, tile); it holds gps UNITS, a unit = 16 columns x one
+// group of 128 channels:
+//   weights  [u = 0..gps-1][c = 0..3][row = 0..15] 16 bytes = 4 words; word j holds the 8 INT4 weights
+//            W[kb .. kb+7][n0 + row], kb = (slice*gps + u)*128 + 32c + 8j, at bit positions
+//            0,16,4,20,8,24,12,28 -- so (w >> 4i) & 0x000F000F is the pair (kb+2i, kb+2i+1) sitting in
+//            the low mantissa bits of a bf16x2 / half2 word, i.e. the payload of one 32-bit TMEM column
+//            of the tcgen05 A operand (lane = output column n, TMEM column = k/2).
+//            One thread dequantises one ROW: 64 contiguous-in-k bytes per unit, read as 4 x 16 B with
+//            the 16 rows of a chunk adjacent (conflict-free 128-bit shared loads).
+//   scales   [u][row] T       s[slice*gps+u][n0+row]                                (gps*32 bytes)
+//   zeros    [u][row] uint8   z[slice*gps+u][n0+row]                                (gps*16 bytes)
 // -> gps * 1072 bytes.  Records are ordered partition-major, then slice, then tile, so the tiles
 // one CTA streams are one contiguous byte range.  A last slice with fewer groups is zero-filled.
 #pragma once
@@ -45,38 +45,27 @@ constexpr int kTileN = 16;
 constexpr int kUnitWeightBytes = 1024;  // 16 columns x 128 channels of INT4
 constexpr int kUnitBytes = 1072;        // + 32 bytes of scales + 16 bytes of zeros
 
-// How the small-M kernel cuts K (a function of K only, so it is part of the layout):
-//   cluster = CTAs that share one range of output tiles and split K between them (thread-block
-//             cluster; partial sums meet through distributed shared memory).  0 = no such
-//             factorisation exists: slices are reduced through a global workspace instead.
-//   warps   = consumer warps per CTA, gpw = groups per warp  ->  gps = warps * gpw
+// How the fused kernel cuts K (a function of K only, so it is part of the layout).  A CTA owns one
+// slice of gps = 8 or 16 groups: 8 groups x 16 output columns fill the 128 TMEM lanes of one
+// tcgen05.mma (every lane = one (column, group) pair; the group's 16 B-operand columns select it).
+//   cluster = number of slices when they fit a thread-block cluster (<= 8): the slices' partial sums
+//             meet through distributed shared memory.  0 = too many slices: global workspace instead.
 struct SlicePlan {
-  int cluster, warps, gpw, gps, slices;
+  int cluster, gps, slices;
 };
 
 inline SlicePlan choose_slice_plan(int groups) {
-  SlicePlan best = {0, 0, 0, 0, 0};
-  int best_score = -1;
-  const int cl[4] = {8, 4, 2, 1};
-  for (int ci = 0; ci < 4; ++ci)
-    for (int gpw = 1; gpw <= 2; ++gpw) {
-      const int c = cl[ci];
-      if (groups % (c * gpw)) continue;
-      const int w = groups / (c * gpw);
-      if (w < 4 || w > 8) continue;
-      const int score = w * 100 + (3 - gpw) * 10 + c;  // more warps, then fewer groups per warp, then wider cluster
-      if (score > best_score) { best_score = score; best = {c, w, gpw, w * gpw, c}; }
-    }
-  if (best_score < 0) {  // e.g. K = 11008 (86 groups): 8-group slices, ragged tail, workspace reduction
-    const int gps = groups >= 8 ? 8 : (groups >= 4 ? 4 : groups);
-    best = {0, gps, 1, gps, (groups + gps - 1) / gps};
-  }
-  const char *e = getenv("PARO_SLICE_PLAN");  // "cluster,warps,gpw" -- experiments only
+  SlicePlan best;
+  const int s8 = (groups + 7) / 8;
+  if (s8 <= 8) best = {s8, 8, s8};                                                // K <= 8192
+  else if (groups % 16 == 0 && groups / 16 <= 8) best = {groups / 16, 16, groups / 16};  // e.g. 12288, 14336
+  else best = {0, 8, s8};                                                         // e.g. 11008 (86 groups)
+  const char *e = getenv("PARO_SLICE_PLAN");  // "gps" -- experiments only
   if (e && *e) {
-    int c = 0, w = 0, g = 0;
-    if (sscanf(e, "%d,%d,%d", &c, &w, &g) == 3 && w >= 1 && w <= 8 && g >= 1 && g <= 2) {
-      const int gps = w * g, s = (groups + gps - 1) / gps;
-      best = {(c >= 1 && c <= 8 && s == c && groups % gps == 0) ? c : 0, w, g, gps, s};
+    const int gps = atoi(e);
+    if (gps == 8 || gps == 16) {
+      const int s = (groups + gps - 1) / gps;
+      best = {s <= 8 ? s : 0, gps, s};
     }
   }
   return best;

@@ -52,13 +52,17 @@ __global__ void prepack_meta_kernel(Layout L, const int16_t *__restrict__ pairs,
       cast_to_T_bits(cscales, static_cast<int64_t>(part) * K + gk * kGroup + c, cs_dtype, L.dtype);
 }
 
+// bit position of k-offset e (0..7) inside a word: consecutive k pairs land in the two 16-bit halves
+// so that (w >> 4i) & 0x000F000F is the bf16x2 / half2 payload of TMEM column i of the word
+__device__ __constant__ int kNibblePos[8] = {0, 16, 4, 20, 8, 24, 12, 28};
+
 __global__ void prepack_weight_kernel(Layout L, PartOffsets po, const int32_t *__restrict__ qweight,
                                       uint8_t *__restrict__ packed) {
-  // one thread per output word: (record, unit u, kh, lane, j)
+  // one thread per output word: (record, unit u, chunk c, row, j)
   const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   const int64_t total = static_cast<int64_t>(L.slices) * L.tiles_total * L.gps * 256;
   if (idx >= total) return;
-  const int j = idx & 3, lane = (idx >> 2) & 31, kh = (idx >> 7) & 1;
+  const int j = idx & 3, row = (idx >> 2) & 15, c = (idx >> 6) & 3;
   const int u = static_cast<int>((idx >> 8) % L.gps);
   const int64_t rec = idx / (256 * static_cast<int64_t>(L.gps));
   // record -> (part, slice, tile)
@@ -67,34 +71,27 @@ __global__ void prepack_weight_kernel(Layout L, PartOffsets po, const int32_t *_
   const int tp = L.part_tile_begin[part + 1] - L.part_tile_begin[part];
   const int64_t rloc = rec - static_cast<int64_t>(L.slices) * L.part_tile_begin[part];
   const int slice = rloc / tp, tile = rloc % tp;
-  const int g = lane >> 2, t = lane & 3;
-  const int n0 = po.n_begin[part] + tile * kTileN;
+  const int n = po.n_begin[part] + tile * kTileN + row;
   const int gk = slice * L.gps + u;
   uint32_t w = 0;
   if (gk < L.groups) {
-    const int64_t kb = static_cast<int64_t>(gk) * kGroup + (kh * 4 + j) * 16;
+    const int64_t kb = static_cast<int64_t>(gk) * kGroup + 32 * c + 8 * j;
     const int nc8 = L.N / 8;
-    w |= awq_nibble(qweight, kb + 2 * t, n0 + g, nc8);
-    w |= awq_nibble(qweight, kb + 2 * t, n0 + g + 8, nc8) << 4;
-    w |= awq_nibble(qweight, kb + 2 * t + 8, n0 + g, nc8) << 8;
-    w |= awq_nibble(qweight, kb + 2 * t + 8, n0 + g + 8, nc8) << 12;
-    w |= awq_nibble(qweight, kb + 2 * t + 1, n0 + g, nc8) << 16;
-    w |= awq_nibble(qweight, kb + 2 * t + 1, n0 + g + 8, nc8) << 20;
-    w |= awq_nibble(qweight, kb + 2 * t + 9, n0 + g, nc8) << 24;
-    w |= awq_nibble(qweight, kb + 2 * t + 9, n0 + g + 8, nc8) << 28;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) w |= awq_nibble(qweight, kb + e, n, nc8) << kNibblePos[e];
   }
   uint32_t *dst = reinterpret_cast<uint32_t *>(packed + L.rec_off + rec * L.rec_bytes);
-  dst[(u * 2 + kh) * 128 + lane * 4 + j] = w;
+  dst[u * 256 + c * 64 + row * 4 + j] = w;
 }
 
 __global__ void prepack_qparam_kernel(Layout L, PartOffsets po, const int32_t *__restrict__ qzeros,
                                       const void *__restrict__ scales, int scales_dtype,
                                       uint8_t *__restrict__ packed) {
-  // one thread per (record, unit u, g, hi)
+  // one thread per (record, unit u, row)
   const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   const int64_t total = static_cast<int64_t>(L.slices) * L.tiles_total * L.gps * 16;
   if (idx >= total) return;
-  const int hi = idx & 1, g = (idx >> 1) & 7;
+  const int row = idx & 15;
   const int u = static_cast<int>((idx >> 4) % L.gps);
   const int64_t rec = idx / (16 * static_cast<int64_t>(L.gps));
   int part = 0;
@@ -102,7 +99,7 @@ __global__ void prepack_qparam_kernel(Layout L, PartOffsets po, const int32_t *_
   const int tp = L.part_tile_begin[part + 1] - L.part_tile_begin[part];
   const int64_t rloc = rec - static_cast<int64_t>(L.slices) * L.part_tile_begin[part];
   const int slice = rloc / tp, tile = rloc % tp;
-  const int n = po.n_begin[part] + tile * kTileN + g + 8 * hi;
+  const int n = po.n_begin[part] + tile * kTileN + row;
   const int gk = slice * L.gps + u;
   uint16_t s = 0;
   uint8_t z = 0;
@@ -111,8 +108,8 @@ __global__ void prepack_qparam_kernel(Layout L, PartOffsets po, const int32_t *_
     z = static_cast<uint8_t>(awq_nibble(qzeros, gk, n, L.N / 8));
   }
   uint8_t *rb = packed + L.rec_off + rec * L.rec_bytes;
-  reinterpret_cast<uint16_t *>(rb + L.gps * kUnitWeightBytes)[(u * 8 + g) * 2 + hi] = s;
-  rb[L.gps * (kUnitWeightBytes + 32) + (u * 8 + g) * 2 + hi] = z;
+  reinterpret_cast<uint16_t *>(rb + L.gps * kUnitWeightBytes)[u * 16 + row] = s;
+  rb[L.gps * (kUnitWeightBytes + 32) + u * 16 + row] = z;
 }
 
 // Inverse, for tests: dense W[k][n] = T((q - z) * s_T), the exact operand the GEMM consumes.
@@ -125,16 +122,14 @@ __global__ void unpack_dense_kernel(Layout L, PartOffsets po, const uint8_t *__r
   int part = 0;
   while (n >= po.n_begin[part + 1]) ++part;
   const int nl = n - po.n_begin[part];
-  const int tile = nl / kTileN, g = nl & 7, hi = (nl >> 3) & 1;
-  const int gk = k / kGroup, slice = gk / L.gps, gw = gk % L.gps, kk = (k % kGroup) / 16, kl = k & 15;
-  const int kh = kk >> 2, j = kk & 3;
-  const int k8 = kl >> 3, t = (kl & 7) >> 1, odd = kl & 1;
-  const int lane = g * 4 + t;
+  const int tile = nl / kTileN, row = nl & 15;
+  const int gk = k / kGroup, slice = gk / L.gps, u = gk % L.gps, kl = k % kGroup;
+  const int c = kl >> 5, j = (kl >> 3) & 3, e = kl & 7;
   const uint8_t *rb = packed + L.record_offset(part, slice, tile);
-  const uint32_t w = reinterpret_cast<const uint32_t *>(rb)[(gw * 2 + kh) * 128 + lane * 4 + j];
-  const int q = (w >> (k8 * 8 + hi * 4 + odd * 16)) & 0xF;
-  const int z = rb[L.gps * (kUnitWeightBytes + 32) + (gw * 8 + g) * 2 + hi];
-  const T s = reinterpret_cast<const T *>(rb + L.gps * kUnitWeightBytes)[(gw * 8 + g) * 2 + hi];
+  const uint32_t w = reinterpret_cast<const uint32_t *>(rb)[u * 256 + c * 64 + row * 4 + j];
+  const int q = (w >> kNibblePos[e]) & 0xF;
+  const int z = rb[L.gps * (kUnitWeightBytes + 32) + u * 16 + row];
+  const T s = reinterpret_cast<const T *>(rb + L.gps * kUnitWeightBytes)[u * 16 + row];
   // (q - z) is exact in T; one rounding in the product, like the fused kernels
   W[idx] = Traits<T>::from_float(static_cast<float>(q - z) * Traits<T>::to_float(s));
 }

@@ -1,0 +1,806 @@
+// Fused small-M path (M <= 16) on 5th-generation tensor cores: scaled pairwise rotation of x +
+// INT4 group dequant + GEMV/GEMM in ONE launch per (merged) linear.  Replaces the reference's
+// rotate -> Marlin kernel pairs (/root/reference/paroquant/inference/backends/vllm/plugin.py:281-311:
+// 2n+1 launches for an n-way merged projection).
+//
+// Why tcgen05 even at batch 1: measured on B200, a warp-level mma.sync.m16n8k16 occupies the legacy
+// HMMA sub-pipe for 32 cycles (sm__pipe_tensor_subpipe_hmma_cycles_active, profiles/), i.e. 256
+// MAC/clk/SM -- at M = 1 that alone is 1.35x the HBM time of the weight stream.  tcgen05.mma runs
+// 4096 MAC/clk/SM and is issued by one thread.
+//
+// Formulation: D[lane, col] += A[lane, k] * B[col, k] with M_mma = 128 lanes, K = 16 per instruction.
+//   lane  = (part p = 0..7, row = 0..15): output column `row` of the current 16-column tile,
+//           restricted to rotation/quantisation group p of the CTA's K-slice.  A[lane, :] are
+//           that row's dequantised weights for the group -- written straight from registers into
+//           TENSOR MEMORY (tcgen05.st), never through shared memory.
+//   col   = (token m, part p'): B[8m + p', k] = x_rot[m][group p'][k], a 16-row smem operand per
+//           k16 step, written once per CTA after the in-kernel rotation.
+//   so D[(p,row), 8m+p] accumulates the dot product of row `row` with token m over group p; the
+//   other columns are ignored.  Eight k16 steps cover the group; the epilogue adds the 8 parts.
+// One tcgen05.mma therefore retires 2048 weights whatever M <= 2 is, and N_mma = 8*Mpad.
+//
+// Roles (320 threads, 2 CTAs / SM, TMEM 256 columns each):
+//   warp 0      producer: cp.async.bulk (TMA) of the CTA's records into an mbarrier ring; issued
+//               before griddepcontrol.wait (weights do not depend on the previous kernel)
+//   warp 1      allocates TMEM; one lane issues tcgen05.mma / tcgen05.commit
+//   warps 2-9   workers, two sets of four (TMEM lane quarter = warp % 4).  Prologue: warp wi owns
+//               group(s) wi (+8): loads x, applies the reference's rotation (rounding points of
+//               rotation.cuh:91-173) with __syncwarp only, writes the B-operand rows.  Main loop:
+//               set e dequantises round r = e, e+2, ...: thread = one (part, row) lane, 16 words ->
+//               64 TMEM columns; then (one round later, so the MMA latency is hidden) reads its D
+//               column back (tcgen05.ld), the 8 parts meet in smem and 16*M threads emit the tile.
+//   K-slices    the `slices` CTAs of a cluster cover K; per-tile partials are pushed through
+//               distributed shared memory to rank (tile mod slices); one cluster barrier; fixed
+//               summation order everywhere (bit-reproducible).  > 8 slices: global workspace.
+//
+// Numerics: x_rot as paro_rotate.cu; W = T((q - z) * T(s)) with ONE rounding, exactly the operand
+// Marlin / AWQ form; fp32 accumulation in TMEM; one rounding to T; bias added in T.
+#include "paro_common.cuh"
+#include "paro_layout.h"
+
+namespace paro {
+
+constexpr int kMaxStages = 8;
+constexpr int kTcThreads = 320;
+constexpr int kTmemCols = 256;
+
+enum ReduceMode { kDirect = 0, kCluster = 1, kWorkspace = 2 };
+
+// Developer aid (PARO_DECODE_TRACE=1): per-CTA phase timestamps of worker warp 0, SM clock cycles
+// relative to kernel entry, + %globaltimer at entry / exit.  Read back with paro_debug_trace().
+constexpr int kTraceSlots = 12;
+constexpr int kTraceMaxCtas = 1024;
+__device__ unsigned long long g_trace[kTraceMaxCtas * kTraceSlots];
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define PARO_TRACE(slot)                                                                                  \
+  do {                                                                                                    \
+    if (p.trace && warp == 2 && lane == 0 && blockIdx.x < kTraceMaxCtas)                                   \
+      g_trace[blockIdx.x * kTraceSlots + (slot)] = static_cast<unsigned long long>(clock64() - t_entry); \
+  } while (0)
+
+struct TcParams {
+  const uint8_t *packed;
+  const void *x;
+  void *y;
+  const void *bias;
+  float *partials;
+  int *counters;
+  int M, K, N;
+  int n_parts, slices, groups, krot, nstages, tiles_total;
+  int gps, nb, rec_bytes, rec_stride;
+  int mpad, nmma, nd;            // padded tokens (2,4,8,16), MMA N = 8*mpad, number of D buffers
+  int mode, rot_bytes, recv_tiles, trace;
+  int xb_off, rot_off, red_off, recv_off, bar_off;  // shared-memory carve-up (bytes)
+  int part_tile_begin[PARO_MAX_PARTS + 1];
+  int part_range_begin[PARO_MAX_PARTS + 1];
+  int meta_group_bytes;
+  long long meta_off, rec_off;
+};
+
+// ------------------------------------------------------------------ tcgen05 wrappers
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem_d] (+)= A[tmem_a] * B[smem desc]; A: 128 lanes x 8 columns (16 x 16-bit k), kind::f16
+__device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld2(uint32_t taddr, uint32_t &a, uint32_t &b) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr) : "memory");
+}
+// K-major, no swizzle: 8-row x 16-byte core matrices; `lbo` = byte distance between the two k-halves
+// of a k16 step, `sbo` = byte distance between 8-row groups (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return static_cast<uint64_t>((addr >> 4) & 0x3FFF) | (static_cast<uint64_t>((lbo >> 4) & 0x3FFF) << 16) |
+         (static_cast<uint64_t>((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (bit 4), a/b format (bits 7, 10: 0 = F16, 1 = BF16), K-major A and B,
+// N >> 3 at bit 17, M >> 4 at bit 24
+template <typename T> __device__ __forceinline__ uint32_t instr_desc(int n) {
+  const uint32_t fmt = Traits<T>::code == PARO_BF16 ? 1u : 0u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (8u << 24);
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// ------------------------------------------------------------------ cluster / DSMEM helpers
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <typename T> __device__ __forceinline__ T bits_to_T(uint32_t b) {
+  const uint16_t h = static_cast<uint16_t>(b);
+  return *reinterpret_cast<const T *>(&h);
+}
+template <typename T> __device__ __forceinline__ uint16_t T_to_bits(T v) { return *reinterpret_cast<const uint16_t *>(&v); }
+
+// ------------------------------------------------------------------ INT4 -> T dequant of one row
+// (a & mask) | magic in ONE LOP3: both constants must sit in registers (LOP3 takes one immediate)
+__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t mask, uint32_t magic) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(mask), "r"(magic));
+  return d;
+}
+
+template <typename T> struct RowDequant;
+
+template <> struct RowDequant<__nv_bfloat16> {
+  uint32_t s2, z2;
+  __device__ __forceinline__ void prep(uint32_t s_bits, uint32_t z) {
+    s2 = s_bits * 0x00010001u;
+    z2 = (0x4300u | z) * 0x00010001u;  // bf16x2 {128 + z, 128 + z}
+  }
+  __device__ __forceinline__ uint32_t one(uint32_t w) const {
+    // 0x4300 | q is the bf16 128 + q; (128 + q) - (128 + z) is exact; one rounding in the multiply
+    const __nv_bfloat162 d = __hsub2(unpack2<__nv_bfloat16>(and_or(w, 0x000F000Fu, 0x43004300u)), unpack2<__nv_bfloat16>(z2));
+    return pack2<__nv_bfloat16>(__hmul2(d, unpack2<__nv_bfloat16>(s2)));
+  }
+  __device__ __forceinline__ void word(uint32_t w, uint32_t *r) const {
+    r[0] = one(w);
+    r[1] = one(w >> 4);
+    r[2] = one(w >> 8);
+    r[3] = one(w >> 12);
+  }
+};
+
+template <> struct RowDequant<__half> {
+  uint32_t s2, z_lo, z_hi16;
+  __device__ __forceinline__ void prep(uint32_t s_bits, uint32_t z) {
+    s2 = s_bits * 0x00010001u;
+    z_lo = (0x6400u | z) * 0x00010001u;           // {1024 + z}
+    z_hi16 = (0xD400u | (z << 4)) * 0x00010001u;  // {-(64 + z)}
+  }
+  __device__ __forceinline__ void word(uint32_t w, uint32_t *r) const {
+    const uint32_t w8 = w >> 8;
+    const __half2 sixteenth = unpack2<__half>(0x2C002C00u), s = unpack2<__half>(s2);
+    // low nibble: 0x6400 | q = 1024 + q.  High nibble in place: 0x6400 | (q << 4) = 1024 + 16 q,
+    // and fma(1024 + 16 q, 1/16, -(64 + z)) = q - z exactly.
+    r[0] = pack2<__half>(__hmul2(__hsub2(unpack2<__half>(and_or(w, 0x000F000Fu, 0x64006400u)), unpack2<__half>(z_lo)), s));
+    r[1] = pack2<__half>(__hmul2(__hfma2(unpack2<__half>(and_or(w, 0x00F000F0u, 0x64006400u)), sixteenth, unpack2<__half>(z_hi16)), s));
+    r[2] = pack2<__half>(__hmul2(__hsub2(unpack2<__half>(and_or(w8, 0x000F000Fu, 0x64006400u)), unpack2<__half>(z_lo)), s));
+    r[3] = pack2<__half>(__hmul2(__hfma2(unpack2<__half>(and_or(w8, 0x00F000F0u, 0x64006400u)), sixteenth, unpack2<__half>(z_hi16)), s));
+  }
+};
+
+// ------------------------------------------------------------------ in-warp rotation of one group
+// Tile `rot` = this warp's [128 channels][ROWS] elements of T, channel-major.  Lane owns pairs
+// 2*lane and 2*lane+1 of every rotation; idxw = bytes (i0, j0, i1, j1).
+template <typename T, int ROWS>
+__device__ __forceinline__ void rotate_stage(uint32_t rot, uint32_t idxw, float c0, float s0, float c1, float s1) {
+  const uint32_t i0 = idxw & 0xFFu, j0 = (idxw >> 8) & 0xFFu, i1 = (idxw >> 16) & 0xFFu, j1 = idxw >> 24;
+  if constexpr (ROWS == 1) {
+    // all four loads first (the two pairs are disjoint), then the math, then the stores
+    const uint32_t a0 = rot + i0 * 2, b0 = rot + j0 * 2, a1 = rot + i1 * 2, b1 = rot + j1 * 2;
+    const float xa0 = Traits<T>::to_float(bits_to_T<T>(lds16(a0))), xb0 = Traits<T>::to_float(bits_to_T<T>(lds16(b0)));
+    const float xa1 = Traits<T>::to_float(bits_to_T<T>(lds16(a1))), xb1 = Traits<T>::to_float(bits_to_T<T>(lds16(b1)));
+    float yi0, yj0, yi1, yj1;
+    givens(c0, s0, xa0, xb0, yi0, yj0);
+    givens(c1, s1, xa1, xb1, yi1, yj1);
+    sts16(a0, T_to_bits<T>(Traits<T>::from_float(yi0)));
+    sts16(b0, T_to_bits<T>(Traits<T>::from_float(yj0)));
+    sts16(a1, T_to_bits<T>(Traits<T>::from_float(yi1)));
+    sts16(b1, T_to_bits<T>(Traits<T>::from_float(yj1)));
+  } else {
+    constexpr int MPW = ROWS / 2;
+    const uint32_t ad[4] = {rot + i0 * (MPW * 4), rot + j0 * (MPW * 4), rot + i1 * (MPW * 4), rot + j1 * (MPW * 4)};
+    uint32_t v[4][MPW];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int u = 0; u < MPW; ++u) v[k][u] = lds32(ad[k] + 4 * u);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float c = q ? c1 : c0, s = q ? s1 : s0;
+#pragma unroll
+      for (int u = 0; u < MPW; ++u) {
+        const float2 a = Traits<T>::to_float2(unpack2<T>(v[2 * q][u]));
+        const float2 b = Traits<T>::to_float2(unpack2<T>(v[2 * q + 1][u]));
+        float yix, yiy, yjx, yjy;
+        givens(c, s, a.x, b.x, yix, yjx);
+        givens(c, s, a.y, b.y, yiy, yjy);
+        sts32(ad[2 * q] + 4 * u, pack2<T>(Traits<T>::from_floats(yix, yiy)));
+        sts32(ad[2 * q + 1] + 4 * u, pack2<T>(Traits<T>::from_floats(yjx, yjy)));
+      }
+    }
+  }
+}
+
+// this lane's 4 channels of the group for all rows: raw x (no dependence on the rotation metadata)
+template <typename T, int ROWS>
+__device__ __forceinline__ void load_x(const TcParams &p, int gk, int lane, uint2 (&raw)[ROWS]) {
+  const T *xg = static_cast<const T *>(p.x) + gk * kGroup + 4 * lane;
+#pragma unroll
+  for (int m = 0; m < ROWS; ++m) {
+    raw[m] = make_uint2(0u, 0u);
+    if (m < p.M) raw[m] = __ldcg(reinterpret_cast<const uint2 *>(xg + static_cast<int64_t>(m) * p.K));
+  }
+}
+
+// multiply by the channel scales in T (one rounding, rotation.cuh:112-113), lay out channel-major in `rot`
+template <typename T, int ROWS>
+__device__ __forceinline__ void scale_and_stage(uint32_t rot, int lane, const uint2 (&raw)[ROWS], uint2 csw) {
+  using T2 = typename Traits<T>::T2;
+  const T2 sc01 = unpack2<T>(csw.x), sc23 = unpack2<T>(csw.y);
+  if constexpr (ROWS == 1) {
+    const uint32_t v01 = pack2<T>(__hmul2(unpack2<T>(raw[0].x), sc01));
+    const uint32_t v23 = pack2<T>(__hmul2(unpack2<T>(raw[0].y), sc23));
+    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(rot + 8 * lane), "r"(v01), "r"(v23) : "memory");
+  } else {
+    constexpr int MPW = ROWS / 2;
+    uint32_t v01[ROWS], v23[ROWS];
+#pragma unroll
+    for (int m = 0; m < ROWS; ++m) {
+      v01[m] = pack2<T>(__hmul2(unpack2<T>(raw[m].x), sc01));
+      v23[m] = pack2<T>(__hmul2(unpack2<T>(raw[m].y), sc23));
+    }
+#pragma unroll
+    for (int u = 0; u < MPW; ++u) {  // word u of a channel = rows (2u, 2u+1)
+      const uint32_t base = rot + (4 * lane) * (MPW * 4) + 4 * u;
+      sts32(base + 0 * (MPW * 4), __byte_perm(v01[2 * u], v01[2 * u + 1], 0x5410));
+      sts32(base + 1 * (MPW * 4), __byte_perm(v01[2 * u], v01[2 * u + 1], 0x7632));
+      sts32(base + 2 * (MPW * 4), __byte_perm(v23[2 * u], v23[2 * u + 1], 0x5410));
+      sts32(base + 3 * (MPW * 4), __byte_perm(v23[2 * u], v23[2 * u + 1], 0x7632));
+    }
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void sincos2(uint32_t theta_pair_bits, float &c0, float &s0, float &c1, float &s1) {
+  const float2 th = Traits<T>::to_float2(unpack2<T>(theta_pair_bits));
+  __sincosf(th.x, &s0, &c0);
+  __sincosf(th.y, &s1, &c1);
+}
+
+// rows of the B operand owned by this warp: B[8m + part][k] = x_rot[m][k] (zero for m >= M / invalid group)
+template <typename T, int ROWS>
+__device__ __forceinline__ void write_b_rows(const TcParams &p, uint32_t xb, uint32_t rot, int part, int b, bool valid, int lane) {
+  const uint32_t step_bytes = p.nmma * 32, lbo = (p.nmma >> 3) * 128;
+  for (int idx = lane; idx < 16 * p.mpad; idx += 32) {
+    const int m = idx >> 4, s = (idx >> 1) & 7, h = idx & 1;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (valid && m < p.M) {
+      const int c0 = 16 * s + 8 * h;
+      if constexpr (ROWS == 1) {
+        v = lds128(rot + c0 * 2);
+      } else {
+        uint32_t e[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) e[k] = lds16(rot + (c0 + k) * (ROWS * 2) + 2 * m);
+        v = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
+      }
+    }
+    const int n = 8 * m + part;
+    sts128u(xb + (b * 8 + s) * step_bytes + h * lbo + (n >> 3) * 128 + (n & 7) * 16, v);
+  }
+}
+
+// full prologue of one worker warp for its nb groups: x, rotation, B rows
+template <typename T, int ROWS>
+__device__ __forceinline__ void rotate_groups(const TcParams &p, int slice, int part_idx, int wi, int lane, uint32_t rot0, uint32_t xb) {
+  uint2 raw[2][ROWS];
+  uint2 csw[2];
+  bool valid[2] = {false, false};
+  const uint8_t *meta[2] = {nullptr, nullptr};
+  for (int b = 0; b < p.nb; ++b) {
+    const int gk = slice * p.gps + b * 8 + wi;
+    valid[b] = gk < p.groups;
+    meta[b] = p.packed + p.meta_off + (static_cast<size_t>(part_idx) * p.groups + (valid[b] ? gk : 0)) * p.meta_group_bytes;
+    csw[b] = make_uint2(0u, 0u);
+    if (valid[b]) {
+      csw[b] = *reinterpret_cast<const uint2 *>(meta[b] + p.krot * 256 + 8 * lane);
+      load_x<T, ROWS>(p, gk, lane, raw[b]);
+    }
+  }
+  for (int b = 0; b < p.nb; ++b)
+    if (valid[b]) scale_and_stage<T, ROWS>(rot0 + b * p.rot_bytes, lane, raw[b], csw[b]);
+  __syncwarp();
+  const int krot = p.krot;
+  for (int r = 0; r < krot; ++r) {
+    for (int b = 0; b < p.nb; ++b)
+      if (valid[b]) {
+        const uint32_t iw = *reinterpret_cast<const uint32_t *>(meta[b] + r * 128 + 4 * lane);
+        const uint32_t tw = *reinterpret_cast<const uint32_t *>(meta[b] + krot * 128 + r * 128 + 4 * lane);
+        float c0, s0, c1, s1;
+        sincos2<T>(tw, c0, s0, c1, s1);
+        rotate_stage<T, ROWS>(rot0 + b * p.rot_bytes, iw, c0, s0, c1, s1);
+      }
+    __syncwarp();
+  }
+  for (int b = 0; b < p.nb; ++b) write_b_rows<T, ROWS>(p, xb, rot0 + b * p.rot_bytes, wi, b, valid[b], lane);
+}
+
+template <typename T>
+__device__ __forceinline__ void store_out(const TcParams &p, float v, int m, int n) {
+  T t = Traits<T>::from_float(v);
+  if (p.bias) t = Traits<T>::from_float(Traits<T>::to_float(t) + Traits<T>::to_float(static_cast<const T *>(p.bias)[n]));  // plugin.py:309-310
+  static_cast<T *>(p.y)[static_cast<int64_t>(m) * p.N + n] = t;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(const TcParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t_entry = clock64();
+  if (p.trace && threadIdx.x == 64 && blockIdx.x < kTraceMaxCtas) g_trace[blockIdx.x * kTraceSlots + 10] = globaltimer_ns();
+  const int nst = p.nstages, nb = p.nb, ND = p.nd;
+  const uint32_t smem0 = smem_u32(smem);
+  const uint32_t xb = smem0 + p.xb_off, rot_all = smem0 + p.rot_off, red = smem0 + p.red_off, recv = smem0 + p.recv_off;
+  const uint32_t bars = smem0 + p.bar_off;
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * kMaxStages;
+  const uint32_t bar_afull = bars + 16 * kMaxStages, bar_afree = bar_afull + 16, bar_dfull = bar_afull + 32, bar_dfree = bar_afull + 48;
+  const uint32_t bar_xb = bar_afull + 64, tmem_slot = bar_afull + 72;
+
+  // ---- which tile range / slice / partition is mine (32-bit arithmetic on launch constants)
+  const int range = blockIdx.x / p.slices;
+  const int slice = blockIdx.x - range * p.slices;  // == %cluster_ctarank in cluster mode
+  int part = 0;
+  while (range >= p.part_range_begin[part + 1]) ++part;
+  const int jl = range - p.part_range_begin[part];
+  const int cp = p.part_range_begin[part + 1] - p.part_range_begin[part];
+  const int tp = p.part_tile_begin[part + 1] - p.part_tile_begin[part];
+  const int t_begin = static_cast<int>(static_cast<unsigned>(jl) * static_cast<unsigned>(tp) / static_cast<unsigned>(cp));
+  const int t_end = static_cast<int>(static_cast<unsigned>(jl + 1) * static_cast<unsigned>(tp) / static_cast<unsigned>(cp));
+  const int ntiles = t_end - t_begin;
+  const int nrounds = ntiles * nb;
+  const int tile_g0 = p.part_tile_begin[part] + t_begin;
+  const uint8_t *rec_src = p.packed + p.rec_off +
+                           (static_cast<size_t>(p.slices) * p.part_tile_begin[part] + static_cast<size_t>(slice) * tp + t_begin) * p.rec_bytes;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nst; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 4 * nb);
+    }
+    for (int e = 0; e < 2; ++e) {
+      mbar_init(bar_afull + 8 * e, 4);
+      mbar_init(bar_afree + 8 * e, 1);
+      mbar_init(bar_dfull + 8 * e, 1);
+      mbar_init(bar_dfree + 8 * e, 4);
+    }
+    mbar_init(bar_xb, 8);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = lds32(tmem_slot);
+  PARO_TRACE(1);
+  if (p.mode == kCluster) cluster_arrive_relaxed();  // #1 "this CTA runs" -- waited on before the first DSMEM push
+  pdl_launch_dependents();                           // let the next linear in the stream start prefetching its weights
+  bool cluster_ready = false;
+
+  if (warp == 0) {
+    // ================= producer: stream the records; nothing here depends on the previous kernel
+    if (lane == 0) {
+      const uint64_t pol = policy_evict_first();
+      for (int i = 0; i < ntiles; ++i) {
+        const int st = i % nst, it = i / nst;
+        if (it > 0) mbar_wait(bar_empty + 8 * st, (it - 1) & 1);
+        mbar_arrive_expect_tx(bar_full + 8 * st, p.rec_bytes);
+        bulk_g2s(smem0 + st * p.rec_stride, rec_src + static_cast<size_t>(i) * p.rec_bytes, p.rec_bytes, bar_full + 8 * st, pol);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc<T>(p.nmma);
+      const uint32_t step_bytes = p.nmma * 32, lbo = (p.nmma >> 3) * 128;
+      mbar_wait(bar_xb, 0);  // B operand rows written (generic proxy) and fenced by the workers
+      for (int r = 0; r < nrounds; ++r) {
+        const int i = r / nb, b = r - i * nb, e = r & 1, d = i % ND;
+        if (b == 0 && i >= ND) mbar_wait(bar_dfree + 8 * d, ((i / ND) - 1) & 1);
+        mbar_wait(bar_afull + 8 * e, (r >> 1) & 1);
+        tc_fence_after();
+        const uint32_t td = tmem + 128 + d * p.nmma, ta = tmem + e * 64;
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+          tc_mma_ts(td, ta + 8 * s, smem_desc_kmajor(xb + (b * 8 + s) * step_bytes, lbo, 128), idesc, (b | s) ? 1u : 0u);
+        tc_commit(bar_afree + 8 * e);
+        if (b == nb - 1) tc_commit(bar_dfull + 8 * d);
+      }
+    }
+  } else {
+    // ================= workers
+    const int wi = warp - 2, e = wi >> 2, q = warp & 3;
+    const int mypart = 2 * q + (lane >> 4), row = lane & 15;
+    const uint32_t rot0 = rot_all + wi * nb * p.rot_bytes;
+    PARO_TRACE(2);
+    pdl_wait();  // x (and the workspace) may have been written by the previous kernel
+    PARO_TRACE(3);
+    {
+      const int M = p.M;
+      if (M == 1) rotate_groups<T, 1>(p, slice, part, wi, lane, rot0, xb);
+      else if (M == 2) rotate_groups<T, 2>(p, slice, part, wi, lane, rot0, xb);
+      else if (M <= 4) rotate_groups<T, 4>(p, slice, part, wi, lane, rot0, xb);
+      else if (M <= 8) rotate_groups<T, 8>(p, slice, part, wi, lane, rot0, xb);
+      else rotate_groups<T, 16>(p, slice, part, wi, lane, rot0, xb);
+    }
+    fence_proxy_async_smem();  // B rows were written through the generic proxy, tcgen05.mma reads them through the async proxy
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_xb);
+    PARO_TRACE(4);
+
+    const uint32_t sc_off = p.gps * kUnitWeightBytes, z_off = p.gps * (kUnitWeightBytes + 32);
+    const uint32_t lane_base = static_cast<uint32_t>(32 * q) << 16;
+    const int tid_set = (wi & 3) * 32 + lane;
+    const int out_per_tile = 16 * p.M;
+    int pend = -1, epi_count = 0;
+
+    auto emit = [&](float v, int tile_local, int o) {
+      const int m = o >> 4, r16 = o & 15;
+      const int tile_g = tile_g0 + tile_local;
+      if (p.mode == kDirect) {
+        store_out<T>(p, v, m, tile_g * kTileN + r16);
+      } else if (p.mode == kCluster) {
+        const uint32_t local = recv + (((tile_local / p.slices) * p.slices + slice) * out_per_tile + o) * 4;
+        st_cluster_f32(map_to_rank(local, tile_local % p.slices), v);
+      } else {
+        __stcg(p.partials + (static_cast<size_t>(slice) * p.tiles_total + tile_g) * out_per_tile + o, v);
+      }
+    };
+
+    auto epilogue = [&](int j) {
+      const int d = j % ND;
+      mbar_wait(bar_dfull + 8 * d, (j / ND) & 1);
+      tc_fence_after();
+      float val[16];
+      const uint32_t tcol = tmem + lane_base + 128 + d * p.nmma + 2 * q;
+#pragma unroll
+      for (int m = 0; m < 16; ++m) {
+        if (m < p.M) {
+          uint32_t v0, v1;
+          tc_ld2(tcol + 8 * m, v0, v1);
+          tc_wait_ld();
+          val[m] = __uint_as_float((lane >> 4) ? v1 : v0);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_dfree + 8 * d);
+      // the 8 parts of a row meet in shared memory: red[buf][m][part][row]
+      const uint32_t rb = red + ((e * 2 + (epi_count & 1)) * 128 * p.M) * 4;
+#pragma unroll
+      for (int m = 0; m < 16; ++m)
+        if (m < p.M) sts_f32(rb + ((m * 8 + mypart) * 16 + row) * 4, val[m]);
+      named_bar_sync(1 + e, 128);
+      if (p.mode == kCluster && !cluster_ready) { cluster_wait_acquire(); cluster_ready = true; }  // #1
+      for (int o = tid_set; o < out_per_tile; o += 128) {
+        const int m = o >> 4, r16 = o & 15;
+        float acc = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) acc += lds_f32(rb + ((m * 8 + pp) * 16 + r16) * 4);  // fixed order
+        emit(acc, j, o);
+      }
+      ++epi_count;
+    };
+
+    bool first = true;
+    for (int r = e; r < nrounds; r += 2) {
+      const int i = r / nb, b = r - i * nb, st = i % nst;
+      mbar_wait(bar_full + 8 * st, (i / nst) & 1);
+      if (first) { PARO_TRACE(5); first = false; }
+      if (r >= 2) mbar_wait(bar_afree + 8 * e, ((r >> 1) - 1) & 1);
+      tc_fence_after();
+      const uint32_t rec = smem0 + st * p.rec_stride;
+      const int u = b * 8 + mypart;
+      RowDequant<T> dq;
+      dq.prep(lds16(rec + sc_off + u * 32 + row * 2), lds8(rec + z_off + u * 16 + row));
+      const uint32_t wbase = rec + u * kUnitWeightBytes + row * 16;
+      const uint32_t ta = tmem + lane_base + e * 64;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint4 w4 = lds128(wbase + c * 256);
+        uint32_t regs[16];
+        dq.word(w4.x, regs + 0);
+        dq.word(w4.y, regs + 4);
+        dq.word(w4.z, regs + 8);
+        dq.word(w4.w, regs + 12);
+        tc_st16(ta + 16 * c, regs);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_afull + 8 * e);
+        mbar_arrive(bar_empty + 8 * st);
+      }
+      if (pend >= 0) { epilogue(pend); pend = -1; }
+      if (b == nb - 1) pend = i;
+    }
+    if (pend >= 0) epilogue(pend);
+    PARO_TRACE(6);
+  }
+
+  // ================= common tail (all threads; warps reconverge first)
+  __syncwarp();
+  if (p.mode == kCluster) {
+    if (!cluster_ready) cluster_wait_acquire();
+    cluster_arrive_release();
+    cluster_wait_acquire();
+    PARO_TRACE(7);
+    if (warp >= 2) {
+      // every CTA finishes the tiles it was sent (tile_local % slices == slice); fixed order over K-slices
+      const int out_per_tile = 16 * p.M;
+      const int nmine = ntiles > slice ? (ntiles - slice + p.slices - 1) / p.slices : 0;
+      for (int idx = threadIdx.x - 64; idx < nmine * out_per_tile; idx += 256) {
+        const int jj = idx / out_per_tile, o = idx - jj * out_per_tile;
+        float acc = 0.f;
+        for (int src = 0; src < p.slices; ++src) acc += lds_f32(recv + ((jj * p.slices + src) * out_per_tile + o) * 4);
+        store_out<T>(p, acc, o >> 4, (tile_g0 + jj * p.slices + slice) * kTileN + (o & 15));
+      }
+    }
+  } else if (p.mode == kWorkspace) {
+    if (warp >= 2) {
+      // announce my tiles; whoever completes a tile sums the slices in fixed order
+      __threadfence();
+      named_bar_sync(3, 256);
+      const int wi = warp - 2, out_per_tile = 16 * p.M;
+      for (int jj = wi; jj < ntiles; jj += 8) {
+        const int tile_g = tile_g0 + jj;
+        int old = 0;
+        if (lane == 0) old = atomicAdd(p.counters + tile_g, 1);
+        old = __shfl_sync(0xFFFFFFFFu, old, 0);
+        if (old != p.slices - 1) continue;
+        __threadfence();
+        for (int o = lane; o < out_per_tile; o += 32) {
+          float acc = 0.f;
+          for (int sl0 = 0; sl0 < p.slices; sl0 += 8) {  // 8 independent loads in flight, then add in order
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              v[k] = sl0 + k < p.slices ? __ldcg(p.partials + (static_cast<size_t>(sl0 + k) * p.tiles_total + tile_g) * out_per_tile + o) : 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc += v[k];
+          }
+          store_out<T>(p, acc, o >> 4, tile_g * kTileN + (o & 15));
+        }
+        if (lane == 0) p.counters[tile_g] = 0;  // leave the workspace zeroed for the next launch
+      }
+    }
+  }
+  PARO_TRACE(8);
+  if (p.trace && warp == 2 && lane == 0 && blockIdx.x < kTraceMaxCtas) g_trace[blockIdx.x * kTraceSlots + 11] = globaltimer_ns();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+  }
+}
+
+int debug_trace_read(unsigned long long *host, int max_ctas) {
+  const size_t n = static_cast<size_t>(max_ctas < kTraceMaxCtas ? max_ctas : kTraceMaxCtas) * kTraceSlots;
+  PARO_CUDA_OK(cudaMemcpyFromSymbol(host, g_trace, n * sizeof(unsigned long long)));
+  return PARO_OK;
+}
+
+// ------------------------------------------------------------------ host side
+struct TcPlan {
+  int ranges;
+  int part_range_begin[PARO_MAX_PARTS + 1];
+  int grid;
+  int max_tiles_per_range;
+};
+
+// Integer number of tile ranges per partition, proportional to the partition's tile count.
+static bool make_plan(const Layout &L, int ranges, TcPlan &plan) {
+  if (ranges < L.n_parts) ranges = L.n_parts;
+  if (ranges > L.tiles_total) ranges = L.tiles_total;
+  int alloc[PARO_MAX_PARTS];
+  double frac[PARO_MAX_PARTS];
+  int used = 0;
+  for (int p = 0; p < L.n_parts; ++p) {
+    const int tp = L.part_tile_begin[p + 1] - L.part_tile_begin[p];
+    const double exact = static_cast<double>(ranges) * tp / L.tiles_total;
+    alloc[p] = static_cast<int>(exact);
+    if (alloc[p] < 1) alloc[p] = 1;
+    if (alloc[p] > tp) alloc[p] = tp;
+    frac[p] = exact - alloc[p];
+    used += alloc[p];
+  }
+  while (used < ranges) {  // largest remainder first
+    int best = -1;
+    for (int p = 0; p < L.n_parts; ++p) {
+      const int tp = L.part_tile_begin[p + 1] - L.part_tile_begin[p];
+      if (alloc[p] < tp && (best < 0 || frac[p] > frac[best])) best = p;
+    }
+    if (best < 0) break;
+    alloc[best]++;
+    frac[best] -= 1.0;
+    used++;
+  }
+  while (used > ranges) {
+    int best = -1;
+    for (int p = 0; p < L.n_parts; ++p)
+      if (alloc[p] > 1 && (best < 0 || frac[p] < frac[best])) best = p;
+    if (best < 0) break;
+    alloc[best]--;
+    frac[best] += 1.0;
+    used--;
+  }
+  plan.part_range_begin[0] = 0;
+  plan.max_tiles_per_range = 0;
+  for (int p = 0; p < PARO_MAX_PARTS; ++p) {
+    plan.part_range_begin[p + 1] = plan.part_range_begin[p] + (p < L.n_parts ? alloc[p] : 0);
+    if (p < L.n_parts) {
+      const int tp = L.part_tile_begin[p + 1] - L.part_tile_begin[p];
+      const int mx = (tp + alloc[p] - 1) / alloc[p];
+      if (mx > plan.max_tiles_per_range) plan.max_tiles_per_range = mx;
+    }
+  }
+  plan.ranges = plan.part_range_begin[L.n_parts];
+  plan.grid = plan.ranges * L.slices;
+  return plan.grid > 0;
+}
+
+size_t decode_workspace_bytes(const Layout &L, int64_t max_m) {
+  const size_t counters = (static_cast<size_t>(L.tiles_total) * 4 + 255) / 256 * 256;
+  if (L.slices <= 1) return counters;
+  return counters + static_cast<size_t>(L.slices) * L.tiles_total * 16 * static_cast<size_t>(max_m) * 4;
+}
+
+static int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+template <typename T>
+static int launch_tc(TcParams &p, const Layout &L, int sms, cudaStream_t stream) {
+  auto kern = tc_linear_kernel<T>;
+  const int ctas_per_sm = env_int("PARO_DECODE_CTAS_PER_SM", 2);
+  const int ranges = sms * ctas_per_sm / L.slices;
+  if (ranges < 1) {
+    set_error("decode: in_features=%d needs %d K-slices, more than the %d resident CTAs", L.K, L.slices, sms * ctas_per_sm);
+    return PARO_EUNSUPPORTED;
+  }
+  const bool want_cluster = L.plan.cluster > 1 && !env_int("PARO_NO_CLUSTER", 0);
+  const int out_per_tile = 16 * p.M;
+  // shared-memory carve-up
+  int off = p.nstages * p.rec_stride;
+  p.xb_off = off;   off += p.nb * 8 * p.nmma * 32;
+  p.rot_off = off;  off += 8 * p.nb * p.rot_bytes;
+  p.red_off = off;  off += 4 * 128 * p.M * 4;
+  p.recv_off = off;
+  TcPlan plan;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if (!make_plan(L, ranges, plan)) { set_error("decode: empty plan"); return PARO_EINVAL; }
+    p.mode = L.slices == 1 ? kDirect : kWorkspace;
+    p.recv_tiles = 0;
+    if (want_cluster && attempt == 0) {
+      const int recv_tiles = (plan.max_tiles_per_range + L.slices - 1) / L.slices;
+      if (static_cast<size_t>(recv_tiles) * L.slices * out_per_tile * 4 <= 40 * 1024) {
+        p.mode = kCluster;
+        p.recv_tiles = recv_tiles;
+      }
+    }
+    p.bar_off = (p.recv_off + p.recv_tiles * L.slices * out_per_tile * 4 + 15) / 16 * 16;
+    const size_t smem = p.bar_off + 16 * kMaxStages + 96;
+    if (smem > 110 * 1024) { set_error("decode: shared-memory footprint %zu too large", smem); return PARO_EUNSUPPORTED; }
+    PARO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(plan.grid);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (p.mode == kCluster) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = L.slices;
+      attr[na].val.clusterDim.y = 1;
+      attr[na].val.clusterDim.z = 1;
+      ++na;
+      // all clusters must be co-resident (one wave): shrink the number of tile ranges if needed
+      int max_clusters = 0;
+      cfg.attrs = attr;
+      cfg.numAttrs = na;
+      const cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
+      if (e != cudaSuccess || max_clusters < L.n_parts) {
+        (void)cudaGetLastError();
+        continue;  // no cluster launch with this footprint: workspace mode
+      }
+      if (max_clusters < plan.ranges) {
+        if (!make_plan(L, max_clusters, plan)) { set_error("decode: empty plan"); return PARO_EINVAL; }
+        if ((plan.max_tiles_per_range + L.slices - 1) / L.slices > p.recv_tiles) continue;  // receive buffer too small now
+        cfg.gridDim = dim3(plan.grid);
+      }
+    }
+    if (!env_int("PARO_NO_PDL", 0)) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    for (int i = 0; i <= PARO_MAX_PARTS; ++i) p.part_range_begin[i] = plan.part_range_begin[i];
+    PARO_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
+    note_launches(1);
+    return PARO_OK;
+  }
+  set_error("decode: no launch configuration found");
+  return PARO_EUNSUPPORTED;
+}
+
+int decode_forward(const paro_linear_shape &s, const Layout &L, const void *packed, const void *x, int64_t M,
+                   const void *bias, void *y, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (workspace_bytes < decode_workspace_bytes(L, M)) {
+    set_error("workspace too small: have %zu, need %zu", workspace_bytes, decode_workspace_bytes(L, M));
+    return PARO_EWORKSPACE;
+  }
+  int dev = 0, sms = 0;
+  PARO_CUDA_OK(cudaGetDevice(&dev));
+  PARO_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  TcParams p;
+  p.packed = static_cast<const uint8_t *>(packed);
+  p.x = x; p.y = y; p.bias = bias;
+  const size_t counters = (static_cast<size_t>(L.tiles_total) * 4 + 255) / 256 * 256;
+  p.counters = static_cast<int *>(workspace);
+  p.partials = reinterpret_cast<float *>(static_cast<uint8_t *>(workspace) + counters);
+  p.M = static_cast<int>(M); p.K = L.K; p.N = L.N;
+  p.n_parts = L.n_parts; p.slices = L.slices; p.groups = L.groups; p.krot = L.krot; p.tiles_total = L.tiles_total;
+  p.gps = L.gps; p.nb = L.gps / 8; p.rec_bytes = L.rec_bytes;
+  p.rec_stride = (L.rec_bytes + 127) / 128 * 128;
+  p.mpad = M <= 2 ? 2 : M <= 4 ? 4 : M <= 8 ? 8 : 16;
+  p.nmma = 8 * p.mpad;
+  p.nd = p.nmma <= 64 ? 2 : 1;
+  int nst = env_int("PARO_DECODE_STAGES", L.gps == 8 ? 6 : 4);
+  if (nst < 2) nst = 2;
+  if (nst > kMaxStages) nst = kMaxStages;
+  p.nstages = nst;
+  p.trace = env_int("PARO_DECODE_TRACE", 0);
+  p.rot_bytes = kGroup * 2 * (M == 1 ? 1 : M == 2 ? 2 : M <= 4 ? 4 : M <= 8 ? 8 : 16);
+  for (int i = 0; i <= PARO_MAX_PARTS; ++i) p.part_tile_begin[i] = L.part_tile_begin[i];
+  p.meta_group_bytes = L.meta_group_bytes;
+  p.meta_off = static_cast<long long>(L.meta_off);
+  p.rec_off = static_cast<long long>(L.rec_off);
+  if (s.dtype == PARO_BF16) return launch_tc<__nv_bfloat16>(p, L, sms, stream);
+  return launch_tc<__half>(p, L, sms, stream);
+}
+
+}  // namespace paro

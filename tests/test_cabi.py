@@ -36,7 +36,7 @@ def test_size_queries_and_shape_errors():
     s = _cabi.make_shape(4096, [4096], 128, 8, torch.bfloat16)
     # 32 groups x 256 tiles x 1072-byte units + 32 groups x (8*256+256) bytes of rotation metadata
     assert _cabi.packed_bytes(s) == 32 * 256 * 1072 + 32 * 2304
-    assert _cabi.workspace_bytes(s, 1) >= 256 * 4 + 4 * 256 * 512   # K = 4096 is cut into 4 slices of 8 groups
+    assert _cabi.workspace_bytes(s, 1) >= 256 * 4 + 4 * 256 * 16 * 4   # K = 4096 is cut into 4 slices of 8 groups
     assert _cabi.workspace_bytes(s, 16) >= _cabi.workspace_bytes(s, 8)
     for bad, msg in ((dict(in_features=4000), "multiple of 128"), (dict(part_sizes=[100]), "multiple of 16"),
                      (dict(group_size=64), "group_size"), (dict(krot=17), "krot")):
