@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(const TcParams
         for (int s = 0; s < 8; ++s)
           tc_mma_ts(td, ta + 8 * s, smem_desc_kmajor(xb + (b * 8 + s) * step_bytes, lbo, 128), idesc, (b | s) ? 1u : 0u);
         tc_commit(bar_afree + 8 * e);
-        if (b == nb - 1) tc_commit(bar_dfull + 8 * d);
+        if (b == nb - 1) tc_commit(bar_dfull + 8 * (r & 1));  // the set that dequantised the last sub-round reads D back
       }
     }
   } else {
@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(const TcParams
 
     auto epilogue = [&](int j) {
       const int d = j % ND;
-      mbar_wait(bar_dfull + 8 * d, (j / ND) & 1);
+      mbar_wait(bar_dfull + 8 * e, epi_count & 1);  // completions of dfull[e] are this set's epilogues, in order
       tc_fence_after();
       float val[16];
       const uint32_t tcol = tmem + lane_base + 128 + d * p.nmma + 2 * q;
@@ -693,20 +693,21 @@ static int env_int(const char *name, int dflt) {
 template <typename T>
 static int launch_tc(TcParams &p, const Layout &L, int sms, cudaStream_t stream) {
   auto kern = tc_linear_kernel<T>;
-  const int ctas_per_sm = env_int("PARO_DECODE_CTAS_PER_SM", 2);
+  const bool want_cluster = L.plan.cluster > 1 && !env_int("PARO_NO_CLUSTER", 0);
+  const int out_per_tile = 16 * p.M;
+  // shared-memory carve-up: [record ring][B operand][rotation tiles, later the 8-part exchange][DSMEM receive][barriers]
+  const int xb_bytes = p.nb * 8 * p.nmma * 32;
+  const int rot_bytes = 8 * p.nb * p.rot_bytes, red_bytes = 4 * 128 * p.M * 4;
+  const int scratch = rot_bytes > red_bytes ? rot_bytes : red_bytes;
+  const int recv_budget = 40 * 1024;
+  int ctas_per_sm = env_int("PARO_DECODE_CTAS_PER_SM", 2);
+  int limit = ctas_per_sm >= 2 ? 110 * 1024 : 220 * 1024;
+  if (xb_bytes + scratch + 2 * p.rec_stride + 4096 > limit) { ctas_per_sm = 1; limit = 220 * 1024; }
   const int ranges = sms * ctas_per_sm / L.slices;
   if (ranges < 1) {
     set_error("decode: in_features=%d needs %d K-slices, more than the %d resident CTAs", L.K, L.slices, sms * ctas_per_sm);
     return PARO_EUNSUPPORTED;
   }
-  const bool want_cluster = L.plan.cluster > 1 && !env_int("PARO_NO_CLUSTER", 0);
-  const int out_per_tile = 16 * p.M;
-  // shared-memory carve-up
-  int off = p.nstages * p.rec_stride;
-  p.xb_off = off;   off += p.nb * 8 * p.nmma * 32;
-  p.rot_off = off;  off += 8 * p.nb * p.rot_bytes;
-  p.red_off = off;  off += 4 * 128 * p.M * 4;
-  p.recv_off = off;
   TcPlan plan;
   for (int attempt = 0; attempt < 2; ++attempt) {
     if (!make_plan(L, ranges, plan)) { set_error("decode: empty plan"); return PARO_EINVAL; }
@@ -714,14 +715,25 @@ static int launch_tc(TcParams &p, const Layout &L, int sms, cudaStream_t stream)
     p.recv_tiles = 0;
     if (want_cluster && attempt == 0) {
       const int recv_tiles = (plan.max_tiles_per_range + L.slices - 1) / L.slices;
-      if (static_cast<size_t>(recv_tiles) * L.slices * out_per_tile * 4 <= 40 * 1024) {
+      if (recv_tiles * L.slices * out_per_tile * 4 <= recv_budget) {
         p.mode = kCluster;
         p.recv_tiles = recv_tiles;
       }
     }
-    p.bar_off = (p.recv_off + p.recv_tiles * L.slices * out_per_tile * 4 + 15) / 16 * 16;
+    const int recv_bytes = p.recv_tiles * L.slices * out_per_tile * 4;
+    const int tail = (recv_bytes + 15) / 16 * 16 + 16 * kMaxStages + 96;
+    int nst = p.nstages;
+    while (nst > 2 && nst * p.rec_stride + xb_bytes + scratch + tail > limit) --nst;
+    if (p.nb == 1 && (nst & 1)) --nst;  // a stage must always be consumed by the same worker set (mbarrier parity)
+    int off = nst * p.rec_stride;
+    p.xb_off = off;  off += xb_bytes;
+    p.rot_off = off; p.red_off = off; off += scratch;   // the exchange buffers reuse the rotation tiles (dead after the prologue)
+    p.recv_off = off;
+    p.bar_off = (off + recv_bytes + 15) / 16 * 16;
     const size_t smem = p.bar_off + 16 * kMaxStages + 96;
-    if (smem > 110 * 1024) { set_error("decode: shared-memory footprint %zu too large", smem); return PARO_EUNSUPPORTED; }
+    if (static_cast<int>(smem) > limit) { set_error("decode: shared-memory footprint %zu too large", smem); return PARO_EUNSUPPORTED; }
+    TcParams q = p;
+    q.nstages = nst;
     PARO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(plan.grid);
@@ -730,7 +742,7 @@ static int launch_tc(TcParams &p, const Layout &L, int sms, cudaStream_t stream)
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     int na = 0;
-    if (p.mode == kCluster) {
+    if (q.mode == kCluster) {
       attr[na].id = cudaLaunchAttributeClusterDimension;
       attr[na].val.clusterDim.x = L.slices;
       attr[na].val.clusterDim.y = 1;
@@ -747,7 +759,7 @@ static int launch_tc(TcParams &p, const Layout &L, int sms, cudaStream_t stream)
       }
       if (max_clusters < plan.ranges) {
         if (!make_plan(L, max_clusters, plan)) { set_error("decode: empty plan"); return PARO_EINVAL; }
-        if ((plan.max_tiles_per_range + L.slices - 1) / L.slices > p.recv_tiles) continue;  // receive buffer too small now
+        if ((plan.max_tiles_per_range + L.slices - 1) / L.slices > q.recv_tiles) continue;  // receive buffer too small now
         cfg.gridDim = dim3(plan.grid);
       }
     }
@@ -758,8 +770,8 @@ static int launch_tc(TcParams &p, const Layout &L, int sms, cudaStream_t stream)
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    for (int i = 0; i <= PARO_MAX_PARTS; ++i) p.part_range_begin[i] = plan.part_range_begin[i];
-    PARO_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
+    for (int i = 0; i <= PARO_MAX_PARTS; ++i) q.part_range_begin[i] = plan.part_range_begin[i];
+    PARO_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, q));
     note_launches(1);
     return PARO_OK;
   }
