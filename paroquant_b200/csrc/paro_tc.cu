@@ -72,7 +72,7 @@ struct TcParams {
   int M, K, N;
   int n_parts, slices, groups, krot, nstages, tiles_total;
   int gps, nb, rec_bytes, rec_stride;
-  int mpad, nmma, nd;            // padded tokens (2,4,8,16), MMA N = 8*mpad, number of D buffers
+  int mpad, nmma, nd, na;        // padded tokens (2,4,8,16), MMA N = 8*mpad, number of D / A buffers in TMEM
   int mode, rot_bytes, recv_tiles, trace;
   int xb_off, rot_off, red_off, recv_off, bar_off;  // shared-memory carve-up (bytes)
   int part_tile_begin[PARO_MAX_PARTS + 1];
@@ -316,39 +316,101 @@ __device__ __forceinline__ void write_b_rows(const TcParams &p, uint32_t xb, uin
   }
 }
 
-// full prologue of one worker warp for its nb groups: x, rotation, B rows
-template <typename T, int ROWS>
-__device__ __forceinline__ void rotate_groups(const TcParams &p, int slice, int part_idx, int wi, int lane, uint32_t rot0, uint32_t xb) {
-  uint2 raw[2][ROWS];
-  uint2 csw[2];
-  bool valid[2] = {false, false};
-  const uint8_t *meta[2] = {nullptr, nullptr};
-  for (int b = 0; b < p.nb; ++b) {
-    const int gk = slice * p.gps + b * 8 + wi;
-    valid[b] = gk < p.groups;
-    meta[b] = p.packed + p.meta_off + (static_cast<size_t>(part_idx) * p.groups + (valid[b] ? gk : 0)) * p.meta_group_bytes;
-    csw[b] = make_uint2(0u, 0u);
-    if (valid[b]) {
-      csw[b] = *reinterpret_cast<const uint2 *>(meta[b] + p.krot * 256 + 8 * lane);
-      load_x<T, ROWS>(p, gk, lane, raw[b]);
+// rotation metadata of this warp's NB groups, fetched (and for NB == 1 run through MUFU) BEFORE
+// griddepcontrol.wait: it does not depend on the previous kernel
+template <int NB> struct RotMeta {
+  uint32_t idxw[NB][8];
+  uint32_t tw[NB][8];      // theta pairs (T bits)
+  float c0[8], s0[8], c1[8], s1[8];  // hoisted coefficients, NB == 1 and krot == 8 only
+  uint2 csw[NB];
+  bool valid[NB];
+  int gk[NB];
+  const uint8_t *meta[NB];
+  bool hoisted;
+};
+
+template <typename T, int NB>
+__device__ __forceinline__ void fetch_rot_meta(const TcParams &p, int slice, int part_idx, int wi, int lane, RotMeta<NB> &rm) {
+  rm.hoisted = (NB == 1) && p.krot == 8;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    rm.gk[b] = slice * p.gps + b * 8 + wi;
+    rm.valid[b] = rm.gk[b] < p.groups;
+    rm.meta[b] = p.packed + p.meta_off + (static_cast<size_t>(part_idx) * p.groups + (rm.valid[b] ? rm.gk[b] : 0)) * p.meta_group_bytes;
+    rm.csw[b] = make_uint2(0u, 0u);
+    if (rm.valid[b]) {
+      rm.csw[b] = *reinterpret_cast<const uint2 *>(rm.meta[b] + p.krot * 256 + 8 * lane);
+      if (p.krot == 8) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          rm.idxw[b][r] = *reinterpret_cast<const uint32_t *>(rm.meta[b] + r * 128 + 4 * lane);
+          rm.tw[b][r] = *reinterpret_cast<const uint32_t *>(rm.meta[b] + 8 * 128 + r * 128 + 4 * lane);
+        }
+      }
     }
   }
-  for (int b = 0; b < p.nb; ++b)
-    if (valid[b]) scale_and_stage<T, ROWS>(rot0 + b * p.rot_bytes, lane, raw[b], csw[b]);
-  __syncwarp();
-  const int krot = p.krot;
-  for (int r = 0; r < krot; ++r) {
-    for (int b = 0; b < p.nb; ++b)
-      if (valid[b]) {
-        const uint32_t iw = *reinterpret_cast<const uint32_t *>(meta[b] + r * 128 + 4 * lane);
-        const uint32_t tw = *reinterpret_cast<const uint32_t *>(meta[b] + krot * 128 + r * 128 + 4 * lane);
-        float c0, s0, c1, s1;
-        sincos2<T>(tw, c0, s0, c1, s1);
-        rotate_stage<T, ROWS>(rot0 + b * p.rot_bytes, iw, c0, s0, c1, s1);
-      }
-    __syncwarp();
+  if constexpr (NB == 1) {
+    if (rm.hoisted && rm.valid[0]) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) sincos2<T>(rm.tw[0][r], rm.c0[r], rm.s0[r], rm.c1[r], rm.s1[r]);
+    }
   }
-  for (int b = 0; b < p.nb; ++b) write_b_rows<T, ROWS>(p, xb, rot0 + b * p.rot_bytes, wi, b, valid[b], lane);
+}
+
+// x-dependent part of the prologue of one worker warp: x, rotation, B rows
+template <typename T, int ROWS, int NB>
+__device__ __forceinline__ void rotate_groups(const TcParams &p, const RotMeta<NB> &rm, int wi, int lane, uint32_t rot0, uint32_t xb) {
+  uint2 raw[NB][ROWS];
+#pragma unroll
+  for (int b = 0; b < NB; ++b)
+    if (rm.valid[b]) load_x<T, ROWS>(p, rm.gk[b], lane, raw[b]);
+#pragma unroll
+  for (int b = 0; b < NB; ++b)
+    if (rm.valid[b]) scale_and_stage<T, ROWS>(rot0 + b * p.rot_bytes, lane, raw[b], rm.csw[b]);
+  __syncwarp();
+  if (p.krot == 8) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b)
+        if (rm.valid[b]) {
+          if (NB == 1 && rm.hoisted) {
+            rotate_stage<T, ROWS>(rot0, rm.idxw[0][r], rm.c0[r], rm.s0[r], rm.c1[r], rm.s1[r]);
+          } else {
+            float c0, s0, c1, s1;
+            sincos2<T>(rm.tw[b][r], c0, s0, c1, s1);
+            rotate_stage<T, ROWS>(rot0 + b * p.rot_bytes, rm.idxw[b][r], c0, s0, c1, s1);
+          }
+        }
+      __syncwarp();
+    }
+  } else {
+    const int krot = p.krot;
+    for (int r = 0; r < krot; ++r) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b)
+        if (rm.valid[b]) {
+          const uint32_t iw = *reinterpret_cast<const uint32_t *>(rm.meta[b] + r * 128 + 4 * lane);
+          const uint32_t tw = *reinterpret_cast<const uint32_t *>(rm.meta[b] + krot * 128 + r * 128 + 4 * lane);
+          float c0, s0, c1, s1;
+          sincos2<T>(tw, c0, s0, c1, s1);
+          rotate_stage<T, ROWS>(rot0 + b * p.rot_bytes, iw, c0, s0, c1, s1);
+        }
+      __syncwarp();
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) write_b_rows<T, ROWS>(p, xb, rot0 + b * p.rot_bytes, wi, b, rm.valid[b], lane);
+}
+
+template <typename T, int NB>
+__device__ __forceinline__ void worker_prologue(const TcParams &p, const RotMeta<NB> &rm, int wi, int lane, uint32_t rot0, uint32_t xb) {
+  const int M = p.M;
+  if (M == 1) rotate_groups<T, 1, NB>(p, rm, wi, lane, rot0, xb);
+  else if (M == 2) rotate_groups<T, 2, NB>(p, rm, wi, lane, rot0, xb);
+  else if (M <= 4) rotate_groups<T, 4, NB>(p, rm, wi, lane, rot0, xb);
+  else if (M <= 8) rotate_groups<T, 8, NB>(p, rm, wi, lane, rot0, xb);
+  else rotate_groups<T, 16, NB>(p, rm, wi, lane, rot0, xb);
 }
 
 template <typename T>
@@ -358,19 +420,22 @@ __device__ __forceinline__ void store_out(const TcParams &p, float v, int m, int
   static_cast<T *>(p.y)[static_cast<int64_t>(m) * p.N + n] = t;
 }
 
-template <typename T>
+template <typename T, int NB>
 __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(const TcParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long t_entry = clock64();
   if (p.trace && threadIdx.x == 64 && blockIdx.x < kTraceMaxCtas) g_trace[blockIdx.x * kTraceSlots + 10] = globaltimer_ns();
-  const int nst = p.nstages, nb = p.nb, ND = p.nd;
+  constexpr int nb = NB;
+  const int nst = p.nstages, ND = p.nd;
   const uint32_t smem0 = smem_u32(smem);
   const uint32_t xb = smem0 + p.xb_off, rot_all = smem0 + p.rot_off, red = smem0 + p.red_off, recv = smem0 + p.recv_off;
   const uint32_t bars = smem0 + p.bar_off;
   const uint32_t bar_full = bars, bar_empty = bars + 8 * kMaxStages;
-  const uint32_t bar_afull = bars + 16 * kMaxStages, bar_afree = bar_afull + 16, bar_dfull = bar_afull + 32, bar_dfree = bar_afull + 48;
-  const uint32_t bar_xb = bar_afull + 64, tmem_slot = bar_afull + 72;
+  const uint32_t bar_afull = bars + 16 * kMaxStages, bar_afree = bar_afull + 32, bar_dfull = bar_afull + 64, bar_dfree = bar_afull + 80;
+  const uint32_t bar_xb = bar_afull + 96, tmem_slot = bar_afull + 104;
+  const int NA = p.na;
+  const uint32_t d_col0 = 64 * NA;
 
   // ---- which tile range / slice / partition is mine (32-bit arithmetic on launch constants)
   const int range = blockIdx.x / p.slices;
@@ -393,9 +458,11 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(const TcParams
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 4 * nb);
     }
+    for (int a = 0; a < 4; ++a) {
+      mbar_init(bar_afull + 8 * a, 4);
+      mbar_init(bar_afree + 8 * a, 1);
+    }
     for (int e = 0; e < 2; ++e) {
-      mbar_init(bar_afull + 8 * e, 4);
-      mbar_init(bar_afree + 8 * e, 1);
       mbar_init(bar_dfull + 8 * e, 1);
       mbar_init(bar_dfree + 8 * e, 4);
     }
@@ -433,15 +500,15 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(const TcParams
       const uint32_t step_bytes = p.nmma * 32, lbo = (p.nmma >> 3) * 128;
       mbar_wait(bar_xb, 0);  // B operand rows written (generic proxy) and fenced by the workers
       for (int r = 0; r < nrounds; ++r) {
-        const int i = r / nb, b = r - i * nb, e = r & 1, d = i % ND;
+        const int i = r / nb, b = r - i * nb, a = r % NA, d = i % ND;
         if (b == 0 && i >= ND) mbar_wait(bar_dfree + 8 * d, ((i / ND) - 1) & 1);
-        mbar_wait(bar_afull + 8 * e, (r >> 1) & 1);
+        mbar_wait(bar_afull + 8 * a, (r / NA) & 1);
         tc_fence_after();
-        const uint32_t td = tmem + 128 + d * p.nmma, ta = tmem + e * 64;
+        const uint32_t td = tmem + d_col0 + d * p.nmma, ta = tmem + a * 64;
 #pragma unroll
         for (int s = 0; s < 8; ++s)
           tc_mma_ts(td, ta + 8 * s, smem_desc_kmajor(xb + (b * 8 + s) * step_bytes, lbo, 128), idesc, (b | s) ? 1u : 0u);
-        tc_commit(bar_afree + 8 * e);
+        tc_commit(bar_afree + 8 * a);
         if (b == nb - 1) tc_commit(bar_dfull + 8 * (r & 1));  // the set that dequantised the last sub-round reads D back
       }
     }
@@ -450,16 +517,13 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(const TcParams
     const int wi = warp - 2, e = wi >> 2, q = warp & 3;
     const int mypart = 2 * q + (lane >> 4), row = lane & 15;
     const uint32_t rot0 = rot_all + wi * nb * p.rot_bytes;
-    PARO_TRACE(2);
-    pdl_wait();  // x (and the workspace) may have been written by the previous kernel
-    PARO_TRACE(3);
     {
-      const int M = p.M;
-      if (M == 1) rotate_groups<T, 1>(p, slice, part, wi, lane, rot0, xb);
-      else if (M == 2) rotate_groups<T, 2>(p, slice, part, wi, lane, rot0, xb);
-      else if (M <= 4) rotate_groups<T, 4>(p, slice, part, wi, lane, rot0, xb);
-      else if (M <= 8) rotate_groups<T, 8>(p, slice, part, wi, lane, rot0, xb);
-      else rotate_groups<T, 16>(p, slice, part, wi, lane, rot0, xb);
+      RotMeta<NB> rm;
+      fetch_rot_meta<T, NB>(p, slice, part, wi, lane, rm);
+      PARO_TRACE(2);
+      pdl_wait();  // x (and the workspace) may have been written by the previous kernel
+      PARO_TRACE(3);
+      worker_prologue<T, NB>(p, rm, wi, lane, rot0, xb);
     }
     fence_proxy_async_smem();  // B rows were written through the generic proxy, tcgen05.mma reads them through the async proxy
     __syncwarp();
@@ -490,7 +554,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(const TcParams
       mbar_wait(bar_dfull + 8 * e, epi_count & 1);  // completions of dfull[e] are this set's epilogues, in order
       tc_fence_after();
       float val[16];
-      const uint32_t tcol = tmem + lane_base + 128 + d * p.nmma + 2 * q;
+      const uint32_t tcol = tmem + lane_base + d_col0 + d * p.nmma + 2 * q;
 #pragma unroll
       for (int m = 0; m < 16; ++m) {
         if (m < p.M) {
@@ -525,14 +589,15 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(const TcParams
       const int i = r / nb, b = r - i * nb, st = i % nst;
       mbar_wait(bar_full + 8 * st, (i / nst) & 1);
       if (first) { PARO_TRACE(5); first = false; }
-      if (r >= 2) mbar_wait(bar_afree + 8 * e, ((r >> 1) - 1) & 1);
+      const int a = r % NA;
+      if (r >= NA) mbar_wait(bar_afree + 8 * a, ((r / NA) - 1) & 1);  // MMAs of round r - NA have drained this A buffer
       tc_fence_after();
       const uint32_t rec = smem0 + st * p.rec_stride;
       const int u = b * 8 + mypart;
       RowDequant<T> dq;
       dq.prep(lds16(rec + sc_off + u * 32 + row * 2), lds8(rec + z_off + u * 16 + row));
       const uint32_t wbase = rec + u * kUnitWeightBytes + row * 16;
-      const uint32_t ta = tmem + lane_base + e * 64;
+      const uint32_t ta = tmem + lane_base + a * 64;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const uint4 w4 = lds128(wbase + c * 256);
@@ -547,7 +612,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(const TcParams
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(bar_afull + 8 * e);
+        mbar_arrive(bar_afull + 8 * a);
         mbar_arrive(bar_empty + 8 * st);
       }
       if (pend >= 0) { epilogue(pend); pend = -1; }
@@ -690,9 +755,9 @@ static int env_int(const char *name, int dflt) {
   return v && *v ? atoi(v) : dflt;
 }
 
-template <typename T>
+template <typename T, int NB>
 static int launch_tc(TcParams &p, const Layout &L, int sms, cudaStream_t stream) {
-  auto kern = tc_linear_kernel<T>;
+  auto kern = tc_linear_kernel<T, NB>;
   const bool want_cluster = L.plan.cluster > 1 && !env_int("PARO_NO_CLUSTER", 0);
   const int out_per_tile = 16 * p.M;
   // shared-memory carve-up: [record ring][B operand][rotation tiles, later the 8-part exchange][DSMEM receive][barriers]
@@ -721,7 +786,7 @@ static int launch_tc(TcParams &p, const Layout &L, int sms, cudaStream_t stream)
       }
     }
     const int recv_bytes = p.recv_tiles * L.slices * out_per_tile * 4;
-    const int tail = (recv_bytes + 15) / 16 * 16 + 16 * kMaxStages + 96;
+    const int tail = (recv_bytes + 15) / 16 * 16 + 16 * kMaxStages + 128;
     int nst = p.nstages;
     while (nst > 2 && nst * p.rec_stride + xb_bytes + scratch + tail > limit) --nst;
     if (p.nb == 1 && (nst & 1)) --nst;  // a stage must always be consumed by the same worker set (mbarrier parity)
@@ -730,7 +795,7 @@ static int launch_tc(TcParams &p, const Layout &L, int sms, cudaStream_t stream)
     p.rot_off = off; p.red_off = off; off += scratch;   // the exchange buffers reuse the rotation tiles (dead after the prologue)
     p.recv_off = off;
     p.bar_off = (off + recv_bytes + 15) / 16 * 16;
-    const size_t smem = p.bar_off + 16 * kMaxStages + 96;
+    const size_t smem = p.bar_off + 16 * kMaxStages + 128;
     if (static_cast<int>(smem) > limit) { set_error("decode: shared-memory footprint %zu too large", smem); return PARO_EUNSUPPORTED; }
     TcParams q = p;
     q.nstages = nst;
@@ -800,7 +865,11 @@ int decode_forward(const paro_linear_shape &s, const Layout &L, const void *pack
   p.rec_stride = (L.rec_bytes + 127) / 128 * 128;
   p.mpad = M <= 2 ? 2 : M <= 4 ? 4 : M <= 8 ? 8 : 16;
   p.nmma = 8 * p.mpad;
-  p.nd = p.nmma <= 64 ? 2 : 1;
+  // TMEM (256 columns per CTA, two CTAs per SM): NA x 64 columns of A + ND x nmma columns of D
+  p.na = env_int("PARO_DECODE_ABUFS", p.nmma <= 64 ? 3 : 2);
+  if (p.na < 2) p.na = 2;
+  if (p.na > 3) p.na = 3;
+  p.nd = (kTmemCols - 64 * p.na) / p.nmma >= 2 ? 2 : 1;
   int nst = env_int("PARO_DECODE_STAGES", L.gps == 8 ? 6 : 4);
   if (nst < 2) nst = 2;
   if (nst > kMaxStages) nst = kMaxStages;
@@ -811,8 +880,8 @@ int decode_forward(const paro_linear_shape &s, const Layout &L, const void *pack
   p.meta_group_bytes = L.meta_group_bytes;
   p.meta_off = static_cast<long long>(L.meta_off);
   p.rec_off = static_cast<long long>(L.rec_off);
-  if (s.dtype == PARO_BF16) return launch_tc<__nv_bfloat16>(p, L, sms, stream);
-  return launch_tc<__half>(p, L, sms, stream);
+  if (s.dtype == PARO_BF16) return p.nb == 1 ? launch_tc<__nv_bfloat16, 1>(p, L, sms, stream) : launch_tc<__nv_bfloat16, 2>(p, L, sms, stream);
+  return p.nb == 1 ? launch_tc<__half, 1>(p, L, sms, stream) : launch_tc<__half, 2>(p, L, sms, stream);
 }
 
 }  // namespace paro
