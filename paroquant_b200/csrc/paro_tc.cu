@@ -499,17 +499,24 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(const TcParams
       const uint32_t idesc = instr_desc<T>(p.nmma);
       const uint32_t step_bytes = p.nmma * 32, lbo = (p.nmma >> 3) * 128;
       mbar_wait(bar_xb, 0);  // B operand rows written (generic proxy) and fenced by the workers
+      int abuf = 0, a_use = 0, dbuf = 0, d_use = 0, i = 0, b = 0;
+#pragma unroll 1
       for (int r = 0; r < nrounds; ++r) {
-        const int i = r / nb, b = r - i * nb, a = r % NA, d = i % ND;
-        if (b == 0 && i >= ND) mbar_wait(bar_dfree + 8 * d, ((i / ND) - 1) & 1);
-        mbar_wait(bar_afull + 8 * a, (r / NA) & 1);
+        if (b == 0 && d_use > 0) mbar_wait(bar_dfree + 8 * dbuf, (d_use - 1) & 1);  // epilogue of the previous user of this D buffer
+        mbar_wait(bar_afull + 8 * abuf, a_use & 1);
         tc_fence_after();
-        const uint32_t td = tmem + d_col0 + d * p.nmma, ta = tmem + a * 64;
+        const uint32_t td = tmem + d_col0 + dbuf * p.nmma, ta = tmem + abuf * 64;
 #pragma unroll
         for (int s = 0; s < 8; ++s)
           tc_mma_ts(td, ta + 8 * s, smem_desc_kmajor(xb + (b * 8 + s) * step_bytes, lbo, 128), idesc, (b | s) ? 1u : 0u);
-        tc_commit(bar_afree + 8 * a);
+        tc_commit(bar_afree + 8 * abuf);
         if (b == nb - 1) tc_commit(bar_dfull + 8 * (r & 1));  // the set that dequantised the last sub-round reads D back
+        if (++abuf == NA) { abuf = 0; ++a_use; }
+        if (++b == nb) {
+          b = 0;
+          ++i;
+          if (++dbuf == ND) { dbuf = 0; ++d_use; }
+        }
       }
     }
   } else {
@@ -530,74 +537,75 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(const TcParams
     if (lane == 0) mbar_arrive(bar_xb);
     PARO_TRACE(4);
 
-    const uint32_t sc_off = p.gps * kUnitWeightBytes, z_off = p.gps * (kUnitWeightBytes + 32);
+    // All loop state is carried incrementally (no integer division in the hot loop).
+    // nb == 1: this set takes tiles e, e+2, ... (sub-round 0);  nb == 2: every tile, sub-round e.
+    constexpr int tile_step = (NB == 1) ? 2 : 1;
+    const int b = (NB == 1) ? 0 : e;
+    const bool does_epilogue = (NB == 1) || e == 1;   // the set that dequantises a tile's last sub-round reads D back
     const uint32_t lane_base = static_cast<uint32_t>(32 * q) << 16;
+    const int u = b * 8 + mypart;
+    const uint32_t unit_off = u * kUnitWeightBytes + row * 16;
+    const uint32_t sc_off = p.gps * kUnitWeightBytes + u * 32 + row * 2, z_off = p.gps * (kUnitWeightBytes + 32) + u * 16 + row;
     const int tid_set = (wi & 3) * 32 + lane;
-    const int out_per_tile = 16 * p.M;
-    int pend = -1, epi_count = 0;
+    const int M = p.M, out_per_tile = 16 * M, mode = p.mode, nslices = p.slices;
+    const uint32_t red_set = red + (e * 2) * 128 * M * 4;
+    const uint32_t my_red = (mypart * 16 + row) * 4;
 
-    auto emit = [&](float v, int tile_local, int o) {
-      const int m = o >> 4, r16 = o & 15;
-      const int tile_g = tile_g0 + tile_local;
-      if (p.mode == kDirect) {
-        store_out<T>(p, v, m, tile_g * kTileN + r16);
-      } else if (p.mode == kCluster) {
-        const uint32_t local = recv + (((tile_local / p.slices) * p.slices + slice) * out_per_tile + o) * 4;
-        st_cluster_f32(map_to_rank(local, tile_local % p.slices), v);
-      } else {
-        __stcg(p.partials + (static_cast<size_t>(slice) * p.tiles_total + tile_g) * out_per_tile + o, v);
-      }
-    };
+    int i = (NB == 1) ? e : 0;                 // current tile (local index)
+    int st = i;                                // its ring stage; nst is even when NB == 1, so parity is per set
+    uint32_t full_par = 0;
+    int abuf = e, a_use = 0;                   // A buffer of round r = i*nb + b (r starts at e), number of earlier uses
+    int i_div = 0, i_mod = i;                  // i / slices, i % slices (slices >= 1)
+    while (i_mod >= nslices) { i_mod -= nslices; ++i_div; }
+    int pend = -1, pend_div = 0, pend_mod = 0, pend_d = 0;
+    uint32_t epi = 0;
 
-    auto epilogue = [&](int j) {
-      const int d = j % ND;
-      mbar_wait(bar_dfull + 8 * e, epi_count & 1);  // completions of dfull[e] are this set's epilogues, in order
+    auto epilogue = [&]() {
+      mbar_wait(bar_dfull + 8 * e, epi & 1);  // completions of dfull[e] are this set's epilogues, in order
       tc_fence_after();
-      float val[16];
-      const uint32_t tcol = tmem + lane_base + d_col0 + d * p.nmma + 2 * q;
-#pragma unroll
-      for (int m = 0; m < 16; ++m) {
-        if (m < p.M) {
-          uint32_t v0, v1;
-          tc_ld2(tcol + 8 * m, v0, v1);
-          tc_wait_ld();
-          val[m] = __uint_as_float((lane >> 4) ? v1 : v0);
-        }
+      const uint32_t rb = red_set + (epi & 1) * 128 * M * 4;
+      const uint32_t tcol = tmem + lane_base + d_col0 + pend_d * p.nmma + 2 * q;
+#pragma unroll 1
+      for (int m = 0; m < M; ++m) {
+        uint32_t v0, v1;
+        tc_ld2(tcol + 8 * m, v0, v1);
+        tc_wait_ld();
+        sts_f32(rb + m * 512 + my_red, __uint_as_float((lane >> 4) ? v1 : v0));  // red[m][part][row]
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_dfree + 8 * d);
-      // the 8 parts of a row meet in shared memory: red[buf][m][part][row]
-      const uint32_t rb = red + ((e * 2 + (epi_count & 1)) * 128 * p.M) * 4;
-#pragma unroll
-      for (int m = 0; m < 16; ++m)
-        if (m < p.M) sts_f32(rb + ((m * 8 + mypart) * 16 + row) * 4, val[m]);
+      if (lane == 0) mbar_arrive(bar_dfree + 8 * pend_d);
       named_bar_sync(1 + e, 128);
-      if (p.mode == kCluster && !cluster_ready) { cluster_wait_acquire(); cluster_ready = true; }  // #1
+      if (mode == kCluster && !cluster_ready) { cluster_wait_acquire(); cluster_ready = true; }  // #1
+#pragma unroll 1
       for (int o = tid_set; o < out_per_tile; o += 128) {
-        const int m = o >> 4, r16 = o & 15;
         float acc = 0.f;
 #pragma unroll
-        for (int pp = 0; pp < 8; ++pp) acc += lds_f32(rb + ((m * 8 + pp) * 16 + r16) * 4);  // fixed order
-        emit(acc, j, o);
+        for (int pp = 0; pp < 8; ++pp) acc += lds_f32(rb + (o >> 4) * 512 + (pp * 16 + (o & 15)) * 4);  // fixed order
+        const int tile_g = tile_g0 + pend;
+        if (mode == kDirect) {
+          store_out<T>(p, acc, o >> 4, tile_g * kTileN + (o & 15));
+        } else if (mode == kCluster) {
+          st_cluster_f32(map_to_rank(recv + ((pend_div * nslices + slice) * out_per_tile + o) * 4, pend_mod), acc);
+        } else {
+          __stcg(p.partials + (static_cast<size_t>(slice) * p.tiles_total + tile_g) * out_per_tile + o, acc);
+        }
       }
-      ++epi_count;
+      ++epi;
     };
 
     bool first = true;
-    for (int r = e; r < nrounds; r += 2) {
-      const int i = r / nb, b = r - i * nb, st = i % nst;
-      mbar_wait(bar_full + 8 * st, (i / nst) & 1);
+#pragma unroll 1
+    for (; i < ntiles; i += tile_step) {
+      mbar_wait(bar_full + 8 * st, full_par);
       if (first) { PARO_TRACE(5); first = false; }
-      const int a = r % NA;
-      if (r >= NA) mbar_wait(bar_afree + 8 * a, ((r / NA) - 1) & 1);  // MMAs of round r - NA have drained this A buffer
+      if (a_use > 0) mbar_wait(bar_afree + 8 * abuf, (a_use - 1) & 1);  // MMAs of the previous user have drained this A buffer
       tc_fence_after();
       const uint32_t rec = smem0 + st * p.rec_stride;
-      const int u = b * 8 + mypart;
       RowDequant<T> dq;
-      dq.prep(lds16(rec + sc_off + u * 32 + row * 2), lds8(rec + z_off + u * 16 + row));
-      const uint32_t wbase = rec + u * kUnitWeightBytes + row * 16;
-      const uint32_t ta = tmem + lane_base + a * 64;
+      dq.prep(lds16(rec + sc_off), lds8(rec + z_off));
+      const uint32_t wbase = rec + unit_off;
+      const uint32_t ta = tmem + lane_base + abuf * 64;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const uint4 w4 = lds128(wbase + c * 256);
@@ -612,13 +620,20 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(const TcParams
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(bar_afull + 8 * a);
+        mbar_arrive(bar_afull + 8 * abuf);
         mbar_arrive(bar_empty + 8 * st);
       }
-      if (pend >= 0) { epilogue(pend); pend = -1; }
-      if (b == nb - 1) pend = i;
+      if (pend >= 0) { epilogue(); pend = -1; }
+      if (does_epilogue) { pend = i; pend_div = i_div; pend_mod = i_mod; pend_d = (ND == 2) ? (i & 1) : 0; }
+      // advance the incremental state
+      st += tile_step;
+      if (st >= nst) { st -= nst; full_par ^= 1; }
+      abuf += 2;
+      if (abuf >= NA) { abuf -= NA; ++a_use; }
+      i_mod += tile_step;
+      while (i_mod >= nslices) { i_mod -= nslices; ++i_div; }
     }
-    if (pend >= 0) epilogue(pend);
+    if (pend >= 0) epilogue();
     PARO_TRACE(6);
   }
 
