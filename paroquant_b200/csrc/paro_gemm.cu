@@ -1,5 +1,21 @@
-// Large-M path (M > 16).  INTERIM: rows are pushed through the fused small-M kernel 16 at a
-// time (correct, weight-stream bound); the tcgen05 GEMM replaces this body.
+// Large-M path (M > 16): rotation pre-pass + INT4-dequant tcgen05 GEMM, tensor-core bound.
+//
+//   y^T[n, m] = sum_k W[n, k] * x_rot[m, k]          (operand-swapped: the quantised weights are the
+//                                                      M_mma = 128 side, the tokens the N side)
+//   A  = W block of 128 output columns x 128 channels per round, dequantised by CUDA cores straight
+//        into TENSOR MEMORY (tcgen05.st): T((q - z) * T(s)), one rounding, the operand Marlin / AWQ form.
+//        No shared-memory round trip and no smem bandwidth spent on the weight operand.
+//   B  = x_rot tile [NT tokens x 64 channels] per stage, produced by the rotation pre-pass
+//        (paro_rotate.cu, the reference's rounding points) directly in UMMA's K-major core-matrix
+//        order, so ONE 1-D bulk copy (TMA) per stage fills the operand -- no tensor map needed.
+//   D  = fp32 [128 x NT] in TMEM (NT <= 256 columns), one rounding to T in the epilogue, bias in T.
+//
+// CTA = one (128-column block of N) x (NT-token block of M) output tile over the whole K.
+// Warp roles as in paro_tc.cu: warp 0 TMA producer (8 x 1 KB weight units + 2 B stages per
+// round), warp 1 TMEM allocator + single-thread tcgen05.mma issuer, warps 2-9 two dequant sets
+// (thread = one output column; round r -> set r & 1, A buffer r % 3), all eight read D back.
+// At NT = 256 one round is 8 MMAs x 128 cycles on the tensor pipe against ~260 dequant
+// instructions per worker thread: the CUDA cores idle, the tensor core does not.
 #include "paro_common.cuh"
 #include "paro_layout.h"
 
@@ -8,19 +24,370 @@ namespace paro {
 size_t decode_workspace_bytes(const Layout &L, int64_t max_m);
 int decode_forward(const paro_linear_shape &s, const Layout &L, const void *packed, const void *x, int64_t M,
                    const void *bias, void *y, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+int rotate_tiled_launch(const void *x, void *out, const int16_t *idx, const void *theta, int theta_dtype, const void *scales,
+                        int scales_dtype, int64_t M, int64_t M_store, int tiled_nt, int K, int krot, int dtype, cudaStream_t stream);
 
-size_t gemm_workspace_bytes(const Layout &L, int64_t max_m) { return decode_workspace_bytes(L, 16); }
+constexpr int kGemmThreads = 320;
+constexpr int kGemmTmemCols = 512;
+constexpr int kWStages = 4;   // rounds of weights in flight (8 KB each)
+constexpr int kBStages = 4;   // k64 stages of x_rot in flight (NT * 128 bytes each)
+constexpr int kABufs = 3;
+
+struct GemmParams {
+  const uint8_t *packed;
+  const uint8_t *xr;       // [n_parts][token blocks][K/16 steps][2][NT/8][8][8] elements
+  void *y;
+  const void *bias;
+  int M, K, N, NT, n_blocks, tok_blocks;
+  int n_parts, slices, groups, gps, rec_bytes, tiles_total;
+  int part_tile_begin[PARO_MAX_PARTS + 1];
+  long long rec_off, xr_part_stride;
+};
+
+// ---- tcgen05 / mbarrier wrappers (same forms as paro_tc.cu)
+__device__ __forceinline__ void g_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void g_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void g_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void g_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void g_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void g_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void g_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void g_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t g_desc_kmajor(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return static_cast<uint64_t>((addr >> 4) & 0x3FFF) | (static_cast<uint64_t>((lbo >> 4) & 0x3FFF) << 16) |
+         (static_cast<uint64_t>((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+template <typename T> __device__ __forceinline__ uint32_t g_instr_desc(int n) {
+  const uint32_t fmt = Traits<T>::code == PARO_BF16 ? 1u : 0u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (8u << 24);
+}
+__device__ __forceinline__ uint32_t g_and_or(uint32_t a, uint32_t mask, uint32_t magic) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(mask), "r"(magic));
+  return d;
+}
+
+// one row's dequant, as in paro_tc.cu
+template <typename T> struct GRowDequant;
+template <> struct GRowDequant<__nv_bfloat16> {
+  uint32_t s2, z2;
+  __device__ __forceinline__ void prep(uint32_t s_bits, uint32_t z) {
+    s2 = s_bits * 0x00010001u;
+    z2 = (0x4300u | z) * 0x00010001u;
+  }
+  __device__ __forceinline__ uint32_t one(uint32_t w) const {
+    const __nv_bfloat162 d = __hsub2(unpack2<__nv_bfloat16>(g_and_or(w, 0x000F000Fu, 0x43004300u)), unpack2<__nv_bfloat16>(z2));
+    return pack2<__nv_bfloat16>(__hmul2(d, unpack2<__nv_bfloat16>(s2)));
+  }
+  __device__ __forceinline__ void word(uint32_t w, uint32_t *r) const {
+    r[0] = one(w); r[1] = one(w >> 4); r[2] = one(w >> 8); r[3] = one(w >> 12);
+  }
+};
+template <> struct GRowDequant<__half> {
+  uint32_t s2, z_lo, z_hi16;
+  __device__ __forceinline__ void prep(uint32_t s_bits, uint32_t z) {
+    s2 = s_bits * 0x00010001u;
+    z_lo = (0x6400u | z) * 0x00010001u;
+    z_hi16 = (0xD400u | (z << 4)) * 0x00010001u;
+  }
+  __device__ __forceinline__ void word(uint32_t w, uint32_t *r) const {
+    const uint32_t w8 = w >> 8;
+    const __half2 sixteenth = unpack2<__half>(0x2C002C00u), s = unpack2<__half>(s2);
+    r[0] = pack2<__half>(__hmul2(__hsub2(unpack2<__half>(g_and_or(w, 0x000F000Fu, 0x64006400u)), unpack2<__half>(z_lo)), s));
+    r[1] = pack2<__half>(__hmul2(__hfma2(unpack2<__half>(g_and_or(w, 0x00F000F0u, 0x64006400u)), sixteenth, unpack2<__half>(z_hi16)), s));
+    r[2] = pack2<__half>(__hmul2(__hsub2(unpack2<__half>(g_and_or(w8, 0x000F000Fu, 0x64006400u)), unpack2<__half>(z_lo)), s));
+    r[3] = pack2<__half>(__hmul2(__hfma2(unpack2<__half>(g_and_or(w8, 0x00F000F0u, 0x64006400u)), sixteenth, unpack2<__half>(z_hi16)), s));
+  }
+};
+
+__device__ __forceinline__ int part_of_tile(const GemmParams &p, int tile_g) {
+  int part = 0;
+  while (part + 1 < p.n_parts && tile_g >= p.part_tile_begin[part + 1]) ++part;
+  return part;
+}
+// byte offset of the record (slice, tile_g) inside packed
+__device__ __forceinline__ size_t record_offset(const GemmParams &p, int slice, int tile_g, int part) {
+  const int tp = p.part_tile_begin[part + 1] - p.part_tile_begin[part];
+  return static_cast<size_t>(p.rec_off) + (static_cast<size_t>(p.slices) * p.part_tile_begin[part] + static_cast<size_t>(slice) * tp +
+                                           (tile_g - p.part_tile_begin[part])) * p.rec_bytes;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const GemmParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NT = p.NT;
+  const uint32_t smem0 = smem_u32(smem);
+  const uint32_t b_stage_bytes = NT * 128;
+  const uint32_t w_ring = smem0, b_ring = smem0 + kWStages * 8192;
+  const uint32_t bars = b_ring + kBStages * b_stage_bytes;
+  const uint32_t bar_wfull = bars, bar_wempty = bars + 32, bar_bfull = bars + 64, bar_bempty = bars + 96;
+  const uint32_t bar_afull = bars + 128, bar_afree = bars + 160, bar_dfull = bars + 192, tmem_slot = bars + 200;
+
+  const int block = blockIdx.x % p.n_blocks, tb = blockIdx.x / p.n_blocks;
+  const int tile0 = block * 8;                                  // first 16-column tile of this 128-column block
+  const int part = part_of_tile(p, tile0);                      // blocks never straddle partitions (host check)
+  const int rounds = p.groups;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWStages; ++s) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, 4); }
+    for (int s = 0; s < kBStages; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
+    for (int a = 0; a < kABufs; ++a) { mbar_init(bar_afull + 8 * a, 4); mbar_init(bar_afree + 8 * a, 1); }
+    mbar_init(bar_dfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kGemmTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  g_fence_before();
+  __syncthreads();
+  g_fence_after();
+  const uint32_t tmem = lds32(tmem_slot);
+  const uint32_t d_col0 = 64 * kABufs;
+
+  if (warp == 0) {
+    // ================= producer: weights do not depend on the pre-pass, x_rot does
+    if (lane == 0) {
+      const uint64_t pol_w = policy_evict_first();
+      const uint8_t *xr_tile = p.xr + static_cast<size_t>(part) * p.xr_part_stride +
+                               static_cast<size_t>(tb) * (p.K / 64) * b_stage_bytes;
+      int valid_tiles = p.tiles_total - tile0;
+      if (valid_tiles > 8) valid_tiles = 8;
+      bool waited = false;
+      for (int r = 0; r < rounds; ++r) {
+        const int ws = r % kWStages, wit = r / kWStages;
+        if (wit > 0) mbar_wait(bar_wempty + 8 * ws, (wit - 1) & 1);
+        const int slice = r / p.gps, u = r - slice * p.gps;
+        mbar_arrive_expect_tx(bar_wfull + 8 * ws, valid_tiles * kUnitWeightBytes);
+        for (int t = 0; t < valid_tiles; ++t)
+          bulk_g2s(w_ring + ws * 8192 + t * kUnitWeightBytes, p.packed + record_offset(p, slice, tile0 + t, part) + u * kUnitWeightBytes,
+                   kUnitWeightBytes, bar_wfull + 8 * ws, pol_w);
+        if (!waited) { pdl_wait(); waited = true; }   // x_rot is written by the pre-pass kernel
+        for (int hstage = 0; hstage < 2; ++hstage) {
+          const int bi = 2 * r + hstage, bs = bi % kBStages, bit = bi / kBStages;
+          if (bit > 0) mbar_wait(bar_bempty + 8 * bs, (bit - 1) & 1);
+          mbar_arrive_expect_tx(bar_bfull + 8 * bs, b_stage_bytes);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(b_ring + bs * b_stage_bytes), "l"(xr_tile + static_cast<size_t>(bi) * b_stage_bytes), "r"(b_stage_bytes),
+                         "r"(bar_bfull + 8 * bs)
+                       : "memory");
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = g_instr_desc<T>(NT);
+      const uint32_t step_bytes = NT * 32, lbo = NT * 16;
+      int abuf = 0, a_use = 0;
+      for (int r = 0; r < rounds; ++r) {
+        mbar_wait(bar_afull + 8 * abuf, a_use & 1);
+        for (int hstage = 0; hstage < 2; ++hstage) {
+          const int bi = 2 * r + hstage, bs = bi % kBStages;
+          mbar_wait(bar_bfull + 8 * bs, (bi / kBStages) & 1);
+          g_fence_after();
+#pragma unroll
+          for (int s4 = 0; s4 < 4; ++s4) {
+            const int s = hstage * 4 + s4;
+            g_mma_ts(tmem + d_col0, tmem + abuf * 64 + 8 * s, g_desc_kmajor(b_ring + bs * b_stage_bytes + s4 * step_bytes, lbo, 128), idesc,
+                     (r | s) ? 1u : 0u);
+          }
+          g_commit(bar_bempty + 8 * bs);
+        }
+        g_commit(bar_afree + 8 * abuf);
+        if (++abuf == kABufs) { abuf = 0; ++a_use; }
+      }
+      g_commit(bar_dfull);
+    }
+  } else {
+    // ================= workers: thread = one output column (TMEM lane)
+    const int wi = warp - 2, e = wi >> 2, q = warp & 3;
+    const int L128 = 32 * q + lane;                // row inside the 128-column block
+    const int tsel = L128 >> 4, row = L128 & 15;   // which of the block's 8 tiles, row inside it
+    const int tile_g = tile0 + tsel;
+    const bool tile_ok = tile_g < p.tiles_total;
+    const uint32_t lane_base = static_cast<uint32_t>(32 * q) << 16;
+    int abuf = e, a_use = 0;
+    for (int r = e; r < rounds; r += 2) {
+      const int ws = r % kWStages;
+      // scale and zero of (this column, group r): small, L2-resident, read straight from the packed records
+      const int slice = r / p.gps, u = r - slice * p.gps;
+      uint32_t sbits = 0, z = 0;
+      if (tile_ok) {
+        const uint8_t *rec = p.packed + record_offset(p, slice, tile_g, part);
+        sbits = *reinterpret_cast<const uint16_t *>(rec + p.gps * kUnitWeightBytes + u * 32 + row * 2);
+        z = rec[p.gps * (kUnitWeightBytes + 32) + u * 16 + row];
+      }
+      mbar_wait(bar_wfull + 8 * ws, (r / kWStages) & 1);
+      if (a_use > 0) mbar_wait(bar_afree + 8 * abuf, (a_use - 1) & 1);
+      g_fence_after();
+      GRowDequant<T> dq;
+      dq.prep(sbits, z);
+      const uint32_t wbase = w_ring + ws * 8192 + tsel * kUnitWeightBytes + row * 16;
+      const uint32_t ta = tmem + lane_base + abuf * 64;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint4 w4 = lds128(wbase + c * 256);
+        uint32_t regs[16];
+        dq.word(w4.x, regs + 0);
+        dq.word(w4.y, regs + 4);
+        dq.word(w4.z, regs + 8);
+        dq.word(w4.w, regs + 12);
+        if (!tile_ok) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) regs[k] = 0u;
+        }
+        g_st16(ta + 16 * c, regs);
+      }
+      g_wait_st();
+      g_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_afull + 8 * abuf);
+        mbar_arrive(bar_wempty + 8 * ws);
+      }
+      abuf += 2;
+      if (abuf >= kABufs) { abuf -= kABufs; ++a_use; }
+    }
+
+    // ---- epilogue: set e converts token columns [e*NT/2, (e+1)*NT/2) of its lanes
+    mbar_wait(bar_dfull, 0);
+    g_fence_after();
+    const int n = block * 128 + L128;
+    const bool n_ok = n < p.N;
+    float bias_f = 0.f;
+    const bool has_bias = p.bias != nullptr;
+    if (has_bias && n_ok) bias_f = Traits<T>::to_float(static_cast<const T *>(p.bias)[n]);
+    T *yout = static_cast<T *>(p.y);
+    const int half_cols = NT / 2;
+    for (int c0 = e * half_cols; c0 < (e + 1) * half_cols; c0 += 16) {
+      uint32_t v[16];
+      g_ld16(tmem + lane_base + d_col0 + c0, v);
+      g_wait_ld();
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int64_t m = static_cast<int64_t>(tb) * NT + c0 + k;
+        if (n_ok && m < p.M) {
+          T t = Traits<T>::from_float(__uint_as_float(v[k]));
+          if (has_bias) t = Traits<T>::from_float(Traits<T>::to_float(t) + bias_f);
+          yout[m * p.N + n] = t;
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  g_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    g_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kGemmTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ host side
+static int pick_nt(int64_t M) { return M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256; }
+
+static bool gemm_supported(const Layout &L) {
+  for (int p = 0; p < L.n_parts; ++p)
+    if ((L.part_tile_begin[p + 1] - L.part_tile_begin[p]) % 8) return p == L.n_parts - 1 && L.n_parts == 1;  // blocks must not straddle partitions
+  return true;
+}
+
+size_t gemm_workspace_bytes(const Layout &L, int64_t max_m) {
+  const size_t small = decode_workspace_bytes(L, 16);
+  if (!gemm_supported(L)) return small;
+  const int NT = pick_nt(max_m);
+  const int64_t m_pad = (max_m + NT - 1) / NT * NT;
+  const size_t xr = static_cast<size_t>(L.n_parts) * m_pad * L.K * 2;
+  return (small + 255) / 256 * 256 + xr;   // x_rot lives behind the small-M region, whose counters must stay zero
+}
+
+template <typename T>
+static int launch_gemm(const GemmParams &p, cudaStream_t stream) {
+  auto kern = tc_gemm_kernel<T>;
+  const size_t smem = kWStages * 8192 + static_cast<size_t>(kBStages) * p.NT * 128 + 256;
+  PARO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.n_blocks * p.tok_blocks);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // prologue + first weight stages overlap the pre-pass
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PARO_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
+  note_launches(1);
+  return PARO_OK;
+}
 
 int gemm_forward(const paro_linear_shape &s, const Layout &L, const void *packed, const void *x, int64_t M,
                  const void *bias, void *y, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
-  const size_t esz = 2;
-  for (int64_t m0 = 0; m0 < M; m0 += 16) {
-    const int64_t mc = M - m0 < 16 ? M - m0 : 16;
-    const int rc = decode_forward(s, L, packed, static_cast<const uint8_t *>(x) + m0 * L.K * esz, mc, bias,
-                                  static_cast<uint8_t *>(y) + m0 * L.N * esz, workspace, workspace_bytes, stream);
+  if (!gemm_supported(L)) {
+    // partition sizes that are not multiples of 128: rows go through the small-M kernel 16 at a time
+    for (int64_t m0 = 0; m0 < M; m0 += 16) {
+      const int64_t mc = M - m0 < 16 ? M - m0 : 16;
+      const int rc = decode_forward(s, L, packed, static_cast<const uint8_t *>(x) + m0 * L.K * 2, mc, bias,
+                                    static_cast<uint8_t *>(y) + m0 * L.N * 2, workspace, workspace_bytes, stream);
+      if (rc) return rc;
+    }
+    return PARO_OK;
+  }
+  if (workspace_bytes < gemm_workspace_bytes(L, M)) {
+    set_error("workspace too small: have %zu, need %zu", workspace_bytes, gemm_workspace_bytes(L, M));
+    return PARO_EWORKSPACE;
+  }
+  const int NT = pick_nt(M);
+  const int64_t m_pad = (M + NT - 1) / NT * NT;
+  const uint8_t *pk = static_cast<const uint8_t *>(packed);
+  uint8_t *xr_base = static_cast<uint8_t *>(workspace) + (decode_workspace_bytes(L, 16) + 255) / 256 * 256;
+  // ---- pre-pass: one rotation per partition, output in B-operand tile order
+  for (int part = 0; part < L.n_parts; ++part) {
+    const uint8_t *raw = pk + L.raw_off + part * L.raw_part_bytes;
+    const int rc = rotate_tiled_launch(x, xr_base + static_cast<size_t>(part) * m_pad * L.K * 2,
+                                       reinterpret_cast<const int16_t *>(raw), raw + static_cast<size_t>(L.krot) * L.K * 2, s.dtype,
+                                       raw + static_cast<size_t>(L.krot) * L.K * 3, s.dtype, M, m_pad, NT, L.K, L.krot, s.dtype, stream);
     if (rc) return rc;
   }
-  return PARO_OK;
+  GemmParams p;
+  p.packed = pk;
+  p.xr = xr_base;
+  p.y = y;
+  p.bias = bias;
+  p.M = static_cast<int>(M); p.K = L.K; p.N = L.N; p.NT = NT;
+  p.n_blocks = (L.tiles_total + 7) / 8;
+  p.tok_blocks = static_cast<int>(m_pad / NT);
+  p.n_parts = L.n_parts; p.slices = L.slices; p.groups = L.groups; p.gps = L.gps; p.rec_bytes = L.rec_bytes; p.tiles_total = L.tiles_total;
+  for (int i = 0; i <= PARO_MAX_PARTS; ++i) p.part_tile_begin[i] = L.part_tile_begin[i];
+  p.rec_off = static_cast<long long>(L.rec_off);
+  p.xr_part_stride = static_cast<long long>(m_pad) * L.K * 2;
+  if (s.dtype == PARO_BF16) return launch_gemm<__nv_bfloat16>(p, stream);
+  return launch_gemm<__half>(p, stream);
 }
 
 }  // namespace paro

@@ -1,6 +1,6 @@
 // The streaming layout paro_prepack writes and both fused kernels read.  Host + device.
 //
-//   packed := [ rotation metadata ][ weight records ]
+//   packed := [ rotation metadata ][ weight records ][ rotation metadata, reference format ]
 //
 // Rotation metadata, one block per (partition p, group gk), groups of 128 channels:
 //   [r = 0..krot-1][128] uint8   pair indices: (i, j) of pair t at bytes 2t, 2t+1
@@ -79,7 +79,7 @@ struct Layout {
   int tiles_total;                         // N / 16
   int part_tile_begin[PARO_MAX_PARTS + 1]; // cumulative tiles per partition
   int meta_group_bytes;                    // krot*256 + 256
-  size_t meta_off, rec_off, total_bytes;
+  size_t meta_off, rec_off, raw_off, raw_part_bytes, total_bytes;  // raw_*: rotation metadata again, in torch.ops.rotation.rotate's own format
 
   PARO_HD size_t meta_offset(int part, int gk) const {
     return meta_off + (static_cast<size_t>(part) * groups + gk) * meta_group_bytes;
@@ -127,7 +127,10 @@ inline bool make_layout(const paro_linear_shape &s, Layout &L, const char **why)
   L.meta_off = 0;
   size_t meta = static_cast<size_t>(s.n_parts) * L.groups * L.meta_group_bytes;
   L.rec_off = (meta + 127) / 128 * 128;
-  L.total_bytes = L.rec_off + static_cast<size_t>(L.slices) * L.tiles_total * L.rec_bytes;
+  L.raw_off = (L.rec_off + static_cast<size_t>(L.slices) * L.tiles_total * L.rec_bytes + 127) / 128 * 128;
+  // per partition: pairs int16 [krot][K], theta T [krot][K/2], channel scales T [K] (the large-M pre-pass reads these)
+  L.raw_part_bytes = (static_cast<size_t>(s.krot) * L.K * 3 + static_cast<size_t>(L.K) * 2 + 127) / 128 * 128;
+  L.total_bytes = L.raw_off + L.raw_part_bytes * s.n_parts;
   return true;
 }
 

@@ -48,8 +48,20 @@ __global__ void prepack_meta_kernel(Layout L, const int16_t *__restrict__ pairs,
       reinterpret_cast<uint16_t *>(blk + L.krot * 128)[r * 64 + c] = cast_to_T_bits(theta, ti, theta_dtype, L.dtype);
     }
   }
-  reinterpret_cast<uint16_t *>(blk + L.krot * 256)[c] =
-      cast_to_T_bits(cscales, static_cast<int64_t>(part) * K + gk * kGroup + c, cs_dtype, L.dtype);
+  const uint16_t csb = cast_to_T_bits(cscales, static_cast<int64_t>(part) * K + gk * kGroup + c, cs_dtype, L.dtype);
+  reinterpret_cast<uint16_t *>(blk + L.krot * 256)[c] = csb;
+  // second copy in the reference op's own format (int16 pairs, [krot][K/2] theta, [K] scales), theta / scales in T
+  uint8_t *raw = packed + L.raw_off + part * L.raw_part_bytes;
+  int16_t *rp = reinterpret_cast<int16_t *>(raw);
+  uint16_t *rt = reinterpret_cast<uint16_t *>(raw + static_cast<size_t>(L.krot) * K * 2);
+  uint16_t *rs = reinterpret_cast<uint16_t *>(raw + static_cast<size_t>(L.krot) * K * 3);
+  for (int r = 0; r < L.krot; ++r) {
+    rp[static_cast<int64_t>(r) * K + gk * kGroup + c] = pairs[(static_cast<int64_t>(part) * L.krot + r) * K + gk * kGroup + c];
+    if (c < 64)
+      rt[static_cast<int64_t>(r) * (K / 2) + gk * 64 + c] =
+          cast_to_T_bits(theta, (static_cast<int64_t>(part) * L.krot + r) * (K / 2) + gk * 64 + c, theta_dtype, L.dtype);
+  }
+  rs[gk * kGroup + c] = csb;
 }
 
 // bit position of k-offset e (0..7) inside a word: consecutive k pairs land in the two 16-bit halves

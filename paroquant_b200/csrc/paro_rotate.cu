@@ -60,7 +60,7 @@ template <typename T, int G>
 __global__ void __launch_bounds__(128) rotate_kernel(const T *__restrict__ x, T *__restrict__ out,
                                                      const int16_t *__restrict__ idx, const void *__restrict__ theta,
                                                      int theta_dtype, const void *__restrict__ scales, int scales_dtype,
-                                                     int64_t M, int K, int krot) {
+                                                     int64_t M, int K, int krot, int64_t M_store, int tiled_nt) {
   constexpr int RB = RotVec<T>::RB;
   constexpr int CPL = G / 32;  // channels per lane for the coalesced load / store
   constexpr int PPL = G / 64;  // pairs per lane
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(128) rotate_kernel(const T *__restrict__ x, T 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int groups = K / G;
   const int64_t task = static_cast<int64_t>(blockIdx.x) * 4 + warp;
-  const int64_t row_blocks = (M + RB - 1) / RB;
+  const int64_t row_blocks = (M_store + RB - 1) / RB;  // rows in [M, M_store) are zero padding (tiled output only)
   if (task >= row_blocks * groups) return;
   const int g = static_cast<int>(task % groups);
   const int64_t row0 = (task / groups) * RB;
@@ -183,13 +183,23 @@ __global__ void __launch_bounds__(128) rotate_kernel(const T *__restrict__ x, T 
     }
 #pragma unroll
     for (int r = 0; r < RB; ++r)
-      if (row0 + r < M) {
+      if (row0 + r < M_store) {
         if constexpr (CPL == 4) {
           uint2 raw;
           T *pr = reinterpret_cast<T *>(&raw);
 #pragma unroll
           for (int c = 0; c < 4; ++c) pr[c] = v[r][c];
-          *reinterpret_cast<uint2 *>(out + (row0 + r) * K + g * G + lane * 4) = raw;
+          if (tiled_nt) {
+            // B-operand order of the tcgen05 GEMM (paro_gemm.cu): [token block][k16 step][k half][n/8][n%8][8 elems]
+            const int64_t m = row0 + r;
+            const int64_t tb = m / tiled_nt;
+            const int n = static_cast<int>(m - tb * tiled_nt), k = g * G + lane * 4;
+            const int64_t off = (tb * (K / 16) + (k >> 4)) * (static_cast<int64_t>(tiled_nt) * 16) + ((k >> 3) & 1) * (tiled_nt * 8) +
+                                (n >> 3) * 64 + (n & 7) * 8 + (k & 7);
+            *reinterpret_cast<uint2 *>(out + off) = raw;
+          } else {
+            *reinterpret_cast<uint2 *>(out + (row0 + r) * K + g * G + lane * 4) = raw;
+          }
         } else {
           uint32_t raw;
           T *pr = reinterpret_cast<T *>(&raw);
@@ -203,9 +213,11 @@ __global__ void __launch_bounds__(128) rotate_kernel(const T *__restrict__ x, T 
 
 template <typename T>
 static int launch_T(const void *x, void *out, const int16_t *idx, const void *theta, int theta_dtype,
-                    const void *scales, int scales_dtype, int64_t M, int K, int krot, int G, cudaStream_t stream) {
+                    const void *scales, int scales_dtype, int64_t M, int K, int krot, int G, cudaStream_t stream,
+                    int64_t M_store = -1, int tiled_nt = 0) {
   constexpr int RB = RotVec<T>::RB;
-  const int64_t tasks = ((M + RB - 1) / RB) * (K / G);
+  if (M_store < 0) M_store = M;
+  const int64_t tasks = ((M_store + RB - 1) / RB) * (K / G);
   const int64_t blocks = (tasks + 3) / 4;
   if (blocks > 0x7FFFFFFF) {
     set_error("rotate: too many rows");
@@ -215,10 +227,10 @@ static int launch_T(const void *x, void *out, const int16_t *idx, const void *th
   T *op = static_cast<T *>(out);
   if (G == 128)
     rotate_kernel<T, 128><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(xp, op, idx, theta, theta_dtype, scales,
-                                                                            scales_dtype, M, K, krot);
+                                                                            scales_dtype, M, K, krot, M_store, tiled_nt);
   else
     rotate_kernel<T, 64><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(xp, op, idx, theta, theta_dtype, scales,
-                                                                           scales_dtype, M, K, krot);
+                                                                           scales_dtype, M, K, krot, M_store, tiled_nt);
   PARO_CUDA_OK(cudaGetLastError());
   note_launches(1);
   return PARO_OK;
@@ -235,6 +247,15 @@ int rotate_launch(const void *x, void *out, const int16_t *idx, const void *thet
   }
   set_error("rotate supports Float, Half, and BFloat16, got dtype code %d", dtype);
   return PARO_EINVAL;
+}
+
+// Rotation pre-pass of the large-M path: the raw metadata of ONE partition, output in the B-operand tile
+// order of the tcgen05 GEMM, zero rows up to M_store (a multiple of tiled_nt).
+int rotate_tiled_launch(const void *x, void *out, const int16_t *idx, const void *theta, int theta_dtype, const void *scales,
+                        int scales_dtype, int64_t M, int64_t M_store, int tiled_nt, int K, int krot, int dtype, cudaStream_t stream) {
+  if (dtype == PARO_F16)
+    return launch_T<__half>(x, out, idx, theta, theta_dtype, scales, scales_dtype, M, K, krot, 128, stream, M_store, tiled_nt);
+  return launch_T<__nv_bfloat16>(x, out, idx, theta, theta_dtype, scales, scales_dtype, M, K, krot, 128, stream, M_store, tiled_nt);
 }
 
 }  // namespace paro

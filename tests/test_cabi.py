@@ -35,7 +35,8 @@ def test_struct_layout_matches_header():
 def test_size_queries_and_shape_errors():
     s = _cabi.make_shape(4096, [4096], 128, 8, torch.bfloat16)
     # 32 groups x 256 tiles x 1072-byte units + 32 groups x (8*256+256) bytes of rotation metadata
-    assert _cabi.packed_bytes(s) == 32 * 256 * 1072 + 32 * 2304
+    raw = lambda K, P: P * ((8 * K * 3 + 2 * K + 127) // 128 * 128)      # reference-format rotation metadata (GEMM pre-pass)
+    assert _cabi.packed_bytes(s) == 32 * 256 * 1072 + 32 * 2304 + raw(4096, 1)
     assert _cabi.workspace_bytes(s, 1) >= 256 * 4 + 4 * 256 * 16 * 4   # K = 4096 is cut into 4 slices of 8 groups
     assert _cabi.workspace_bytes(s, 16) >= _cabi.workspace_bytes(s, 8)
     for bad, msg in ((dict(in_features=4000), "multiple of 128"), (dict(part_sizes=[100]), "multiple of 16"),
@@ -50,7 +51,7 @@ def test_size_queries_and_shape_errors():
 
 def test_merged_layout_is_partition_major():
     s = _cabi.make_shape(4096, [4096, 1024, 1024], 128, 8, torch.float16)
-    assert _cabi.packed_bytes(s) == 32 * 384 * 1072 + ((3 * 32 * 2304 + 127) // 128) * 128
+    assert _cabi.packed_bytes(s) == 32 * 384 * 1072 + ((3 * 32 * 2304 + 127) // 128) * 128 + 3 * ((8 * 4096 * 3 + 2 * 4096 + 127) // 128 * 128)
 
 
 def test_cpu_tensors_are_rejected_loudly():

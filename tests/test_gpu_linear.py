@@ -183,3 +183,39 @@ def test_vs_reference_pipeline_fixture(PK, path):
     W = k.dense_weight().cpu()
     wref = torch.from_numpy(np.ascontiguousarray(z["w_onehot"])).view(torch.int16).view(_TD[dt])
     assert torch.equal(W[torch.from_numpy(z["w_rows"])], wref)
+
+
+@pytest.mark.parametrize("dt", ["bfloat16", "float16"])
+@pytest.mark.parametrize("K,parts,M", [(512, [128], 17), (1024, [256, 128], 40), (1024, [256, 128], 64), (4096, [1024], 100),
+                                       (4096, [4096], 256), (4096, [4096, 1024, 1024], 300), (11008, [512], 33), (14336, [256], 257)])
+def test_large_m_gemm_vs_rotate_and_dense(PK, dt, K, parts, M):
+    """M > 16: rotation pre-pass + tcgen05 GEMM against fp64 matmul on the kernel's own dequantised operand and the
+    standalone rotate kernel (both bit-checked elsewhere); ragged M (not a multiple of the token tile), merged
+    projections, ragged K-slices, partial 128-column blocks."""
+    import paroquant_b200.kernels.cuda  # noqa: F401
+    L = make_synthetic_layer(K, parts, seed=53, device="cuda", bias=(M == 40))
+    k = PK.from_buffers(L, _TD[dt], max_m=M)
+    W = k.dense_weight().double()
+    x = make_synthetic_activations(M, K, seed=70 + M, device="cuda", dtype=_TD[dt])
+    bias = None if L.bias is None else L.bias.to(_TD[dt])
+    y = k(x, bias)
+    n0, chunks = 0, []
+    for p, n in enumerate(parts):
+        xr = torch.ops.rotation.rotate(x, L.pairs[p], L.theta[p], L.channel_scales[p]).double()
+        chunks.append(xr @ W[:, n0:n0 + n])
+        n0 += n
+    ref = torch.cat(chunks, -1).float().to(_TD[dt])
+    if bias is not None:
+        ref = (ref.float() + bias.float()).to(_TD[dt])
+    err = ((y.double() - ref.double()).norm() / ref.double().norm()).item()
+    assert err < 3e-4, err
+    assert torch.equal(k(x, bias), y)
+
+
+def test_large_m_vs_oracle(PK, oracle):
+    L = make_synthetic_layer(1024, [256, 128], seed=59)
+    k = PK.from_buffers(L.to("cuda"), torch.bfloat16, max_m=48)
+    x = make_synthetic_activations(48, 1024, seed=12)
+    y = k(x.cuda()).float().cpu().numpy()
+    ref = oracle.linear(x.float().numpy(), L.numpy_dict(), "bfloat16")
+    assert oracle.rel_err(y, ref) < TOL
