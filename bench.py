@@ -227,11 +227,50 @@ def run_ours(args):
                          "traffic": None, "peak_source": src, "kernel": "paro::decode_kernel", "launches_per_step": launches_per_step,
                          "algorithmic_bytes_per_step": step_bytes, "avg_launch_us": ms * 1e3 / max(launches_per_step, 1)},
         }
+        if world == 1 and not args.no_prefill:
+            line["prefill"] = prefill_section(dev)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample(M)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def prefill_section(dev):
+    """BASELINE.json config 2 beside the decode headline: fused rotate + dequant + tcgen05 GEMM at batch 4096 on the
+    Llama-3-8B linear shapes, TFLOP/s against the measured bf16 tensor roofline (each call: rotation pre-pass + GEMM)."""
+    import torch
+
+    from paroquant_b200 import _cabi
+    from paroquant_b200.checkpoint import make_synthetic_activations, make_synthetic_layer
+    from paroquant_b200.linear import ParoLinearKernel
+
+    _, tf_peak, src = measured_peaks()
+    out, tot_fl, tot_us = {}, 0.0, 0.0
+    Mp = 4096
+    for name, (K, parts, _) in SHAPES.items():
+        k = ParoLinearKernel.from_buffers(make_synthetic_layer(K, parts, seed=99, device=dev), torch.bfloat16, check_pairs=False, max_m=Mp)
+        x = make_synthetic_activations(Mp, K, seed=5, device=dev)
+        y = torch.empty(Mp, sum(parts), dtype=torch.bfloat16, device=dev)
+        for _ in range(3):
+            _cabi.linear_forward(k.shape, k.packed, x, None, k.workspace, out=y)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            _cabi.linear_forward(k.shape, k.packed, x, None, k.workspace, out=y)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / reps
+        fl = 2.0 * Mp * K * sum(parts)
+        out[name] = {"us": us, "tflops": fl / us / 1e6}
+        tot_fl += fl
+        tot_us += us
+        del k, x, y
+        torch.cuda.empty_cache()
+    return {"batch": Mp, "tflops": tot_fl / tot_us / 1e6, "frac_tensor": tot_fl / tot_us / 1e6 / tf_peak, "peak_tflops": tf_peak,
+            "peak_source": src, "per_linear": out, "note": "one Llama-3-8B layer's quantised linears at 4096 tokens, rotation pre-pass included"}
 
 
 # ------------------------------------------------------------------------------------------ CPU baseline / reference arm
@@ -297,6 +336,7 @@ def main():
     ap.add_argument("--m", type=int, default=1, help="decode batch (rows per linear), 1..16")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prefill", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
