@@ -12,8 +12,8 @@
 //
 // CTA = one (128-column block of N) x (NT-token block of M) output tile over the whole K.
 // Warp roles as in paro_tc.cu: warp 0 TMA producer (8 x 1 KB weight units + 2 B stages per
-// round), warp 1 TMEM allocator + single-thread tcgen05.mma issuer, warps 2-9 two dequant sets
-// (thread = one output column; round r -> set r & 1, A buffer r % 3), all eight read D back.
+// round), warp 1 TMEM allocator + single-thread tcgen05.mma issuer, warps 2-17 four dequant sets
+// (thread = one output column; round r -> set r % 4, A buffer r % 3), all of them read D back.
 // At NT = 256 one round is 8 MMAs x 128 cycles on the tensor pipe against ~260 dequant
 // instructions per worker thread: the CUDA cores idle, the tensor core does not.
 #include "paro_common.cuh"
@@ -27,7 +27,8 @@ int decode_forward(const paro_linear_shape &s, const Layout &L, const void *pack
 int rotate_tiled_launch(const void *x, void *out, const int16_t *idx, const void *theta, int theta_dtype, const void *scales,
                         int scales_dtype, int64_t M, int64_t M_store, int tiled_nt, int K, int krot, int dtype, cudaStream_t stream);
 
-constexpr int kGemmThreads = 320;
+constexpr int kGemmSets = 4;                       // dequant sets of 4 warps; round r -> set r % 4
+constexpr int kGemmThreads = 32 * (2 + 4 * kGemmSets);
 constexpr int kGemmTmemCols = 512;
 constexpr int kWStages = 4;   // rounds of weights in flight (8 KB each)
 constexpr int kBStages = 4;   // k64 stages of x_rot in flight (NT * 128 bytes each)
@@ -230,17 +231,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const GemmPara
     const int tile_g = tile0 + tsel;
     const bool tile_ok = tile_g < p.tiles_total;
     const uint32_t lane_base = static_cast<uint32_t>(32 * q) << 16;
-    int abuf = e, a_use = 0;
-    for (int r = e; r < rounds; r += 2) {
-      const int ws = r % kWStages;
-      // scale and zero of (this column, group r): small, L2-resident, read straight from the packed records
-      const int slice = r / p.gps, u = r - slice * p.gps;
-      uint32_t sbits = 0, z = 0;
-      if (tile_ok) {
+    // scale and zero of (this column, group r): small and L2-resident, read straight from the packed records,
+    // always one of this set's rounds ahead so the latency never sits in front of the dequant
+    auto fetch_qparam = [&](int r, uint32_t &sbits, uint32_t &z) {
+      sbits = 0; z = 0;
+      if (tile_ok && r < rounds) {
+        const int slice = r / p.gps, u = r - slice * p.gps;
         const uint8_t *rec = p.packed + record_offset(p, slice, tile_g, part);
         sbits = *reinterpret_cast<const uint16_t *>(rec + p.gps * kUnitWeightBytes + u * 32 + row * 2);
         z = rec[p.gps * (kUnitWeightBytes + 32) + u * 16 + row];
       }
+    };
+    uint32_t sbits, z, sbits_next, z_next;
+    fetch_qparam(e, sbits, z);
+    int abuf = e % kABufs, a_use = e / kABufs;
+    for (int r = e; r < rounds; r += kGemmSets) {
+      const int ws = r % kWStages;
+      fetch_qparam(r + kGemmSets, sbits_next, z_next);
       mbar_wait(bar_wfull + 8 * ws, (r / kWStages) & 1);
       if (a_use > 0) mbar_wait(bar_afree + 8 * abuf, (a_use - 1) & 1);
       g_fence_after();
@@ -269,11 +276,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const GemmPara
         mbar_arrive(bar_afull + 8 * abuf);
         mbar_arrive(bar_wempty + 8 * ws);
       }
-      abuf += 2;
+      sbits = sbits_next;
+      z = z_next;
+      abuf += kGemmSets % kABufs;                 // (r + 4) % 3 and (r + 4) / 3, carried incrementally
+      a_use += kGemmSets / kABufs;
       if (abuf >= kABufs) { abuf -= kABufs; ++a_use; }
     }
 
-    // ---- epilogue: set e converts token columns [e*NT/2, (e+1)*NT/2) of its lanes
+    // ---- epilogue: set e converts its share of the token columns of its lanes
     mbar_wait(bar_dfull, 0);
     g_fence_after();
     const int n = block * 128 + L128;
@@ -282,8 +292,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const GemmPara
     const bool has_bias = p.bias != nullptr;
     if (has_bias && n_ok) bias_f = Traits<T>::to_float(static_cast<const T *>(p.bias)[n]);
     T *yout = static_cast<T *>(p.y);
-    const int half_cols = NT / 2;
-    for (int c0 = e * half_cols; c0 < (e + 1) * half_cols; c0 += 16) {
+    const int set_cols = NT / kGemmSets >= 16 ? NT / kGemmSets : 16;   // token columns this set converts
+    for (int c0 = e * set_cols; c0 < (e + 1) * set_cols && c0 < NT; c0 += 16) {
       uint32_t v[16];
       g_ld16(tmem + lane_base + d_col0 + c0, v);
       g_wait_ld();
