@@ -28,9 +28,9 @@ int rotate_tiled_launch(const void *x, void *out, const int16_t *idx, const void
                         int scales_dtype, int64_t M, int64_t M_store, int tiled_nt, int K, int krot, int dtype, cudaStream_t stream);
 
 constexpr int kGemmSets = 4;                       // dequant sets of 4 warps; round r -> set r % 4
-constexpr int kGemmThreads = 32 * (2 + 4 * kGemmSets);
+constexpr int kGemmThreads = 32 * (3 + 4 * kGemmSets);   // + weight producer, MMA issuer, x_rot producer
 constexpr int kGemmTmemCols = 512;
-constexpr int kWStages = 4;   // rounds of weights in flight (8 KB each)
+constexpr int kWStages = 8;   // rounds of weights in flight (8 KB each); a multiple of kGemmSets
 constexpr int kBStages = 4;   // k64 stages of x_rot in flight (NT * 128 bytes each)
 constexpr int kABufs = 3;
 
@@ -144,8 +144,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const GemmPara
   const uint32_t b_stage_bytes = NT * 128;
   const uint32_t w_ring = smem0, b_ring = smem0 + kWStages * 8192;
   const uint32_t bars = b_ring + kBStages * b_stage_bytes;
-  const uint32_t bar_wfull = bars, bar_wempty = bars + 32, bar_bfull = bars + 64, bar_bempty = bars + 96;
-  const uint32_t bar_afull = bars + 128, bar_afree = bars + 160, bar_dfull = bars + 192, tmem_slot = bars + 200;
+  const uint32_t bar_wfull = bars, bar_wempty = bars + 64, bar_bfull = bars + 128, bar_bempty = bars + 160;
+  const uint32_t bar_afull = bars + 192, bar_afree = bars + 224, bar_dfull = bars + 256, tmem_slot = bars + 264;
 
   const int block = blockIdx.x % p.n_blocks, tb = blockIdx.x / p.n_blocks;
   const int tile0 = block * 8;                                  // first 16-column tile of this 128-column block
@@ -170,32 +170,38 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const GemmPara
   const uint32_t d_col0 = 64 * kABufs;
 
   if (warp == 0) {
-    // ================= producer: weights do not depend on the pre-pass, x_rot does
+    // ================= weight producer: independent of the pre-pass; every 128-column block is re-read by
+    // all token blocks, so the units stay under the normal L2 policy (no evict-first here)
     if (lane == 0) {
-      const uint64_t pol_w = policy_evict_first();
-      const uint8_t *xr_tile = p.xr + static_cast<size_t>(part) * p.xr_part_stride +
-                               static_cast<size_t>(tb) * (p.K / 64) * b_stage_bytes;
       int valid_tiles = p.tiles_total - tile0;
       if (valid_tiles > 8) valid_tiles = 8;
-      bool waited = false;
       for (int r = 0; r < rounds; ++r) {
         const int ws = r % kWStages, wit = r / kWStages;
         if (wit > 0) mbar_wait(bar_wempty + 8 * ws, (wit - 1) & 1);
         const int slice = r / p.gps, u = r - slice * p.gps;
         mbar_arrive_expect_tx(bar_wfull + 8 * ws, valid_tiles * kUnitWeightBytes);
         for (int t = 0; t < valid_tiles; ++t)
-          bulk_g2s(w_ring + ws * 8192 + t * kUnitWeightBytes, p.packed + record_offset(p, slice, tile0 + t, part) + u * kUnitWeightBytes,
-                   kUnitWeightBytes, bar_wfull + 8 * ws, pol_w);
-        if (!waited) { pdl_wait(); waited = true; }   // x_rot is written by the pre-pass kernel
-        for (int hstage = 0; hstage < 2; ++hstage) {
-          const int bi = 2 * r + hstage, bs = bi % kBStages, bit = bi / kBStages;
-          if (bit > 0) mbar_wait(bar_bempty + 8 * bs, (bit - 1) & 1);
-          mbar_arrive_expect_tx(bar_bfull + 8 * bs, b_stage_bytes);
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(b_ring + bs * b_stage_bytes), "l"(xr_tile + static_cast<size_t>(bi) * b_stage_bytes), "r"(b_stage_bytes),
-                         "r"(bar_bfull + 8 * bs)
+                       ::"r"(w_ring + ws * 8192 + t * kUnitWeightBytes),
+                         "l"(p.packed + record_offset(p, slice, tile0 + t, part) + u * kUnitWeightBytes), "r"(kUnitWeightBytes),
+                         "r"(bar_wfull + 8 * ws)
                        : "memory");
-        }
+      }
+    }
+  } else if (warp == kGemmThreads / 32 - 1) {
+    // ================= x_rot producer: one contiguous NT x 64 operand tile per stage
+    if (lane == 0) {
+      const uint8_t *xr_tile = p.xr + static_cast<size_t>(part) * p.xr_part_stride +
+                               static_cast<size_t>(tb) * (p.K / 64) * b_stage_bytes;
+      pdl_wait();   // x_rot is written by the pre-pass kernel
+      for (int bi = 0; bi < 2 * rounds; ++bi) {
+        const int bs = bi % kBStages, bit = bi / kBStages;
+        if (bit > 0) mbar_wait(bar_bempty + 8 * bs, (bit - 1) & 1);
+        mbar_arrive_expect_tx(bar_bfull + 8 * bs, b_stage_bytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(b_ring + bs * b_stage_bytes), "l"(xr_tile + static_cast<size_t>(bi) * b_stage_bytes), "r"(b_stage_bytes),
+                       "r"(bar_bfull + 8 * bs)
+                     : "memory");
       }
     }
   } else if (warp == 1) {
@@ -339,7 +345,7 @@ size_t gemm_workspace_bytes(const Layout &L, int64_t max_m) {
 template <typename T>
 static int launch_gemm(const GemmParams &p, cudaStream_t stream) {
   auto kern = tc_gemm_kernel<T>;
-  const size_t smem = kWStages * 8192 + static_cast<size_t>(kBStages) * p.NT * 128 + 256;
+  const size_t smem = kWStages * 8192 + static_cast<size_t>(kBStages) * p.NT * 128 + 512;
   PARO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(p.n_blocks * p.tok_blocks);
