@@ -31,7 +31,14 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-HIDDEN, KV, INTER, LAYERS = 4096, 1024, 14336, 32
+HIDDEN, KV, INTER = 4096, 1024, 14336
+LAYERS = int(os.environ.get("BENCH_LAYERS", "32"))   # 32 = Llama-3-8B; smaller only for smoke-testing the harness
+_VERBOSE = os.environ.get("BENCH_VERBOSE") == "1"
+
+
+def _log(msg):
+    if _VERBOSE:
+        print(f"[bench r{os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
 SHAPES = {  # name: (K, part_sizes, kind)
     "qkv": (HIDDEN, [HIDDEN, KV, KV], "col"), "o": (HIDDEN, [HIDDEN], "row"),
     "gate_up": (HIDDEN, [INTER, INTER], "col"), "down": (INTER, [HIDDEN], "row"),
@@ -107,6 +114,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        _log("process group up")
     M = args.m
     dt = torch.bfloat16
 
@@ -127,6 +135,7 @@ def run_ours(args):
             del buf
         layers.append(lk)
     torch.cuda.synchronize()
+    _log("weights prepacked")
     xs = {name: make_synthetic_activations(M, shard(name)[0], seed=77 + i, device=dev, dtype=dt) for i, name in enumerate(SHAPES)}
     outs = {name: torch.empty(M, sum(shard(name)[1]), dtype=dt, device=dev) for name in SHAPES}
     x_host = make_synthetic_activations(M, HIDDEN, seed=77, dtype=dt).pin_memory()
@@ -154,6 +163,7 @@ def run_ours(args):
             token()
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
+    _log("eager warm-up done")
     use_graph = not args.no_graph
     if use_graph:
         graph = torch.cuda.CUDAGraph()
@@ -168,9 +178,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    _log("graph captured" if use_graph else "eager mode")
     for _ in range(max(args.warmup, 3)):
         run_step()
     barrier()
+    _log("warm-up done")
     sampler = ClockSampler(local)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -180,6 +192,7 @@ def run_ours(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
+    _log(f"timed region done: {ms:.3f} ms/step")
     # keep the identical load running briefly so the NVML sampler sees clocks under this workload
     t_end = time.time() + 0.6
     while time.time() < t_end:
@@ -216,7 +229,7 @@ def run_ours(args):
             "metric": "llama3_8b_int4_decode_tokens_per_s", "value": M * 1e3 / ms, "unit": "tokens/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"Llama-3-8B all quantised linears, decode batch {M}: 32 x (qkv 4096->6144 P=3, o 4096->4096, "
+            "config": {"workload": f"Llama-3-8B all quantised linears, decode batch {M}: {LAYERS} x (qkv 4096->6144 P=3, o 4096->4096, "
                                    f"gate_up 4096->28672 P=2, down 14336->4096), INT4 g128 krot8, fused rotate+dequant+GEMV",
                        "batch": M, "parallelism": f"tp{world}", "launch": "cuda_graph+pdl" if use_graph else "eager+pdl",
                        "l2": "3.66 GB of weights streamed per step >> 126 MB L2, no flush needed"},
@@ -233,7 +246,13 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline_sample(M)
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # destroy_process_group() can block for minutes in the NCCL heartbeat monitor once torchrun's TCPStore
+        # goes away (seen on the 2-GPU box: all work done, processes never exit).  Everything is flushed: leave.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def prefill_section(dev):
