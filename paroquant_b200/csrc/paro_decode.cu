@@ -1,0 +1,668 @@
+// Fused small-M path, second generation (M <= 16): scaled pairwise rotation of x + INT4 group dequant
+// + GEMV/GEMM in ONE launch per (merged) linear, ONE persistent CTA per SM.  Replaces the reference's
+// rotate -> Marlin kernel pairs (/root/reference/paroquant/inference/backends/vllm/plugin.py:281-311).
+//
+// Formulation (operand-swapped, as the large-M kernel): D[n, m] += W[n, k] * x_rot[m, k]
+//   A = 128 output columns x 128 channels (one quantisation group) per ROUND, dequantised by CUDA cores
+//       straight into TENSOR MEMORY (tcgen05.st); thread = one output column = one TMEM lane.
+//   B = x_rot of the CTA's K-slice, 16 token rows (zero-padded), written once per CTA after the in-kernel
+//       rotation, UMMA K-major core-matrix order.
+//   D = fp32 [128 x 16] in TMEM, double buffered.  All rounds of a 128-column block accumulate into the
+//       SAME D whichever dequant set produced the A operand: the tensor core does the in-CTA part of the
+//       split-K reduction, and the result is read back ONCE per block (tcgen05.ld, one value per thread
+//       and token) -- no shared-memory exchange, no intra-CTA barrier in the main loop.
+//
+// Work split: the `c` CTAs of a cluster cover K (ragged slices of whole groups); a cluster walks a range
+// of 128-column blocks of one partition.  Cross-slice partials are pushed through distributed shared
+// memory to rank (block mod c); one cluster barrier; fixed summation order (bit-reproducible).
+//
+// Roles (SETS x 4 dequant warps + 2): warps 0..4*SETS-1 workers (TMEM lane quarter = warp % 4): the
+// prologue rotates the slice's groups (one group per warp, __syncwarp only); the main loop takes rounds
+// r = set, set + SETS, ...; the set that dequantised a block's last group reads D back.  Warp 4*SETS:
+// TMA producer (8 x 1 KB unit copies per round into an mbarrier ring, issued before
+// griddepcontrol.wait).  Warp 4*SETS+1: TMEM allocator + single-thread tcgen05.mma issuer.
+//
+// Numerics: x_rot as paro_rotate.cu; W = T((q - z) * T(s)) with ONE rounding (the operand Marlin / AWQ
+// form); fp32 accumulation in TMEM; one rounding to T; bias added in T (plugin.py:309-310).
+#include <cstdio>
+
+#include "paro_tc_common.cuh"
+
+namespace paro {
+
+constexpr int kDecMaxStages = 24;
+constexpr int kDecTmemCols = 512;
+constexpr int kDecN = 16;            // MMA N: token rows, zero-padded (M_mma = 128 needs N % 16 == 0)
+constexpr int kDecSmemLimit = 227 * 1024;
+
+constexpr int kDecTraceSlots = 12;
+constexpr int kDecTraceMaxCtas = 256;   // rows 200.. double as a per-round log of CTA 0 (issue / full / consumed)
+__device__ unsigned long long g_dec_trace[kDecTraceMaxCtas * kDecTraceSlots];
+#define DEC_TRACE(slot)                                                                                      \
+  do {                                                                                                       \
+    if (p.trace && warp == 0 && lane == 0 && blockIdx.x < 200)                                   \
+      g_dec_trace[blockIdx.x * kDecTraceSlots + (slot)] = static_cast<unsigned long long>(clock64() - t_entry); \
+  } while (0)
+
+struct DecParams {
+  const uint8_t *packed;
+  const void *x;
+  void *y;
+  const void *bias;
+  int M, K, N;
+  int n_parts, groups, krot, gps, gps_shift, lslices, rec_bytes;
+  int c, c_shift;                 // cluster size (K slices of this launch), log2
+  int nstages, rot_bytes, trace;
+  int nacc, fake1;                // independent accumulators per D buffer (k16 step s -> accumulator s % nacc); experiment switch
+  int xb_off, scratch_off, bar_off;   // shared-memory carve-up (bytes); scratch = rotation tiles, later the DSMEM receive buffer
+  int part_tile_begin[PARO_MAX_PARTS + 1];
+  int part_range_begin[PARO_MAX_PARTS + 1];
+  int meta_group_bytes;
+  long long meta_off, rec_off;
+};
+
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// ---- prologue of one worker warp: groups gi = wi, wi + W, ... of the CTA's slice -> B operand rows
+// B[gi][k16 step s][k half h][row m][8 k]: 16 rows x 16 bytes per core-matrix pair, 512 bytes per step
+template <typename T, int ROWS>
+__device__ __forceinline__ void dec_write_b_rows(uint32_t xb_group, uint32_t rot, int M, int lane) {
+  for (int idx = lane; idx < 16 * kDecN; idx += 32) {
+    const int m = idx >> 4, s = (idx >> 1) & 7, h = idx & 1;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (m < M) {
+      const int c0 = 16 * s + 8 * h;
+      if constexpr (ROWS == 1) {
+        v = lds128(rot + c0 * 2);
+      } else {
+        uint32_t e[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) e[k] = lds16(rot + (c0 + k) * (ROWS * 2) + 2 * m);
+        v = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
+      }
+    }
+    sts128u(xb_group + s * (kDecN * 32) + h * (kDecN * 16) + (m >> 3) * 128 + (m & 7) * 16, v);
+  }
+}
+
+struct DecRotMeta {
+  uint32_t idxw[8], tw[8];
+  uint2 csw;
+  const uint8_t *meta;
+};
+
+__device__ __forceinline__ void dec_fetch_meta(const DecParams &p, int part, int gk, int lane, DecRotMeta &rm) {
+  rm.meta = p.packed + p.meta_off + (static_cast<size_t>(part) * p.groups + gk) * p.meta_group_bytes;
+  rm.csw = *reinterpret_cast<const uint2 *>(rm.meta + p.krot * 256 + 8 * lane);
+  if (p.krot == 8) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      rm.idxw[r] = *reinterpret_cast<const uint32_t *>(rm.meta + r * 128 + 4 * lane);
+      rm.tw[r] = *reinterpret_cast<const uint32_t *>(rm.meta + 8 * 128 + r * 128 + 4 * lane);
+    }
+  }
+}
+
+template <typename T, int ROWS>
+__device__ __forceinline__ void dec_rotate_group(const DecParams &p, const DecRotMeta &rm, int gk, int lane, uint32_t rot, uint32_t xb_group,
+                                                 long long t_entry) {
+  uint2 raw[ROWS];
+  load_x<T, ROWS>(p, gk, lane, raw);
+  scale_and_stage<T, ROWS>(rot, lane, raw, rm.csw);
+  __syncwarp();
+  if (p.trace && threadIdx.x == 0 && blockIdx.x < 200) g_dec_trace[blockIdx.x * kDecTraceSlots + 0] = clock64() - t_entry;
+  if (p.krot == 8) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      float c0, s0, c1, s1;
+      sincos2<T>(rm.tw[r], c0, s0, c1, s1);
+      rotate_stage<T, ROWS>(rot, rm.idxw[r], c0, s0, c1, s1);
+      __syncwarp();
+    }
+  } else {
+    const int krot = p.krot;
+    for (int r = 0; r < krot; ++r) {
+      const uint32_t iw = *reinterpret_cast<const uint32_t *>(rm.meta + r * 128 + 4 * lane);
+      const uint32_t tw = *reinterpret_cast<const uint32_t *>(rm.meta + krot * 128 + r * 128 + 4 * lane);
+      float c0, s0, c1, s1;
+      sincos2<T>(tw, c0, s0, c1, s1);
+      rotate_stage<T, ROWS>(rot, iw, c0, s0, c1, s1);
+      __syncwarp();
+    }
+  }
+  if (p.trace && threadIdx.x == 0 && blockIdx.x < 200) g_dec_trace[blockIdx.x * kDecTraceSlots + 9] = clock64() - t_entry;
+  dec_write_b_rows<T, ROWS>(xb_group, rot, p.M, lane);
+  __syncwarp();
+}
+
+template <typename T, int ROWS>
+__device__ __forceinline__ void dec_prologue(const DecParams &p, DecRotMeta &rm, int part, int g_begin, int ng, int wi, int nworkers,
+                                             int lane, uint32_t rot, uint32_t xb, long long t_entry) {
+  for (int gi = wi; gi < ng; gi += nworkers) {
+    if (gi != wi) dec_fetch_meta(p, part, g_begin + gi, lane, rm);   // the first group's metadata was fetched before the wait
+    dec_rotate_group<T, ROWS>(p, rm, g_begin + gi, lane, rot, xb + gi * (kDecN * 256), t_entry);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void dec_store(const DecParams &p, float v, int m, int n) {
+  T t = Traits<T>::from_float(v);
+  if (p.bias) t = Traits<T>::from_float(Traits<T>::to_float(t) + Traits<T>::to_float(static_cast<const T *>(p.bias)[n]));  // plugin.py:309-310
+  static_cast<T *>(p.y)[static_cast<int64_t>(m) * p.N + n] = t;
+}
+
+template <typename T, int SETS>
+__global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const DecParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int kWorkers = 4 * SETS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t_entry = clock64();
+  if (p.trace && threadIdx.x == 0 && blockIdx.x < 200) g_dec_trace[blockIdx.x * kDecTraceSlots + 10] = globaltimer_ns();
+  const int NS = p.nstages;
+  const uint32_t smem0 = smem_u32(smem);
+  const uint32_t xb = smem0 + p.xb_off, scratch = smem0 + p.scratch_off, bars = smem0 + p.bar_off;
+  const uint32_t bar_wfull = bars, bar_wempty = bars + 8 * kDecMaxStages;
+  const uint32_t bar_afull = bars + 16 * kDecMaxStages, bar_afree = bar_afull + 64;
+  const uint32_t bar_dfull = bar_afull + 128, bar_dfree = bar_afull + 144, bar_xb = bar_afull + 160, tmem_slot = bar_afull + 168;
+  constexpr uint32_t d_col0 = 64 * SETS;
+
+  // ---- my range of 128-column blocks (within one partition) and my K-slice (whole groups, ragged)
+  const int range = blockIdx.x >> p.c_shift;
+  const int slice = blockIdx.x & (p.c - 1);   // == %cluster_ctarank
+  int part = 0;
+  while (range >= p.part_range_begin[part + 1]) ++part;
+  const int jl = range - p.part_range_begin[part];
+  const int cp = p.part_range_begin[part + 1] - p.part_range_begin[part];
+  const int tp = p.part_tile_begin[part + 1] - p.part_tile_begin[part];
+  const int cbp = tp >> 3;
+  const int cb_begin = static_cast<int>(static_cast<unsigned>(jl) * static_cast<unsigned>(cbp) / static_cast<unsigned>(cp));
+  const int cb_end = static_cast<int>(static_cast<unsigned>(jl + 1) * static_cast<unsigned>(cbp) / static_cast<unsigned>(cp));
+  const int nj = cb_end - cb_begin;
+  const int g_begin = static_cast<int>(static_cast<unsigned>(slice) * static_cast<unsigned>(p.groups) >> p.c_shift);
+  const int g_end = static_cast<int>(static_cast<unsigned>(slice + 1) * static_cast<unsigned>(p.groups) >> p.c_shift);
+  const int ng = g_end - g_begin;
+  const int nrounds = nj * ng;
+  // records of this partition: (L-slice, tile) -> rec_part + (lslice * tp + tile_in_part) * rec_bytes
+  const uint8_t *rec_part = p.packed + p.rec_off + static_cast<size_t>(p.lslices) * p.part_tile_begin[part] * p.rec_bytes;
+
+  DecRotMeta rm;
+  if (warp < kWorkers && warp < ng) dec_fetch_meta(p, part, g_begin + warp, lane, rm);   // flies during the barrier init / TMEM allocation
+
+  if (warp == kWorkers) {
+    // one barrier per lane
+    if (lane < NS) {
+      mbar_init(bar_wfull + 8 * lane, 1);
+      mbar_init(bar_wempty + 8 * lane, 4);
+    }
+    if (lane < SETS) {
+      mbar_init(bar_afull + 8 * lane, 4);
+      mbar_init(bar_afree + 8 * lane, 1);
+    }
+    if (lane < 2) {
+      mbar_init(bar_dfull + 8 * lane, 1);
+      mbar_init(bar_dfree + 8 * lane, 4);
+    }
+    if (lane == 0) mbar_init(bar_xb, kWorkers);
+    fence_mbar_init();
+  }
+  if (warp == kWorkers + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kDecTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = lds32(tmem_slot);
+  DEC_TRACE(1);
+  pdl_launch_dependents();   // let the next linear in the stream start prefetching its weights
+  bool cluster_ready = false;
+
+  if (warp == kWorkers) {
+    // ================= producer: 8 unit copies per round, one per lane; nothing here depends on the previous kernel
+    if (p.c > 1) cluster_arrive_release();   // #1 (the workers arrive once their rotation tiles are dead)
+    const uint64_t pol = policy_evict_first();
+    int st = 0, it = 0, j = 0, gi = 0;
+    for (int r = 0; r < nrounds; ++r) {
+      if (lane < 8) {
+        if (it > 0) mbar_wait(bar_wempty + 8 * st, (it - 1) & 1);
+        const int g = g_begin + gi, ls = g >> p.gps_shift, u = g & (p.gps - 1);
+        const uint8_t *src = rec_part + (static_cast<size_t>(ls) * tp + (cb_begin + j) * 8 + lane) * p.rec_bytes + u * kUnitWeightBytes;
+        if (lane == 0) mbar_arrive_expect_tx(bar_wfull + 8 * st, 8 * kUnitWeightBytes);
+        if (p.trace && lane == 0 && blockIdx.x == 0 && r < 100) g_dec_trace[200 * kDecTraceSlots + 3 * r] = clock64() - t_entry;
+        if (p.fake1) {   // timing experiment only (wrong data): one 8 KB copy per round
+          if (lane == 0) bulk_g2s(smem0 + st * 8192, rec_part + static_cast<size_t>(cb_begin * ng + r) * 8192, 8192, bar_wfull + 8 * st, pol);
+        } else {
+          bulk_g2s(smem0 + st * 8192 + lane * kUnitWeightBytes, src, kUnitWeightBytes, bar_wfull + 8 * st, pol);
+        }
+      }
+      if (++st == NS) { st = 0; ++it; }
+      if (++gi == ng) { gi = 0; ++j; }
+    }
+  } else if (warp == kWorkers + 1) {
+    // ================= MMA issuer.  The whole warp runs the loop (waits included) and ONE elected lane issues:
+    // inside an `elect.sync` region ptxas keeps descriptors and TMEM addresses in uniform registers; under a plain
+    // `lane == 0` branch every tcgen05.mma was wrapped in a divergence loop (~15 instructions, ~120 cycles per MMA,
+    // tools/mma_probe.cu) and the single issuing thread, not the tensor pipe, bounded the kernel.
+    if (p.c > 1) cluster_arrive_release();   // #1
+    {
+      const uint32_t idesc = instr_desc<T>(kDecN);
+      mbar_wait(bar_xb, 0);   // B operand rows written (generic proxy) and fenced by the workers
+      const int nacc = p.nacc;
+      const uint64_t desc_hi = smem_desc_kmajor(0, kDecN * 16, 128);   // everything but the start address
+      int set = 0, use = 0, j = 0, gi = 0;
+#pragma unroll 1
+      for (int r = 0; r < nrounds; ++r) {
+        if (gi == 0 && j >= 2) mbar_wait(bar_dfree + 8 * (j & 1), ((j >> 1) - 1) & 1);   // D buffer read back by its previous user
+        mbar_wait(bar_afull + 8 * set, use & 1);
+        tc_fence_after();
+        // consecutive k16 steps go to `nacc` independent accumulators, summed (fixed order) when D is read back
+        const uint32_t td = tmem + d_col0 + (j & 1) * (nacc * kDecN), ta = tmem + set * 64;
+        const uint64_t bdesc0 = desc_hi | static_cast<uint64_t>(((xb + gi * (kDecN * 256)) >> 4) & 0x3FFF);
+        if (elect_one()) {
+#pragma unroll
+          for (int s = 0; s < 8; ++s)
+            tc_mma_ts(td + (s & (nacc - 1)) * kDecN, ta + 8 * s, bdesc0 + s * ((kDecN * 32) >> 4), idesc, (gi != 0 || s >= nacc) ? 1u : 0u);
+          tc_commit(bar_afree + 8 * set);
+          if (gi == ng - 1) tc_commit(bar_dfull + 8 * (j & 1));
+        }
+        __syncwarp();
+        if (++set == SETS) { set = 0; ++use; }
+        if (++gi == ng) { gi = 0; ++j; }
+      }
+    }
+  } else {
+    // ================= workers
+    const int wi = warp, e = wi >> 2, q = warp & 3;
+    const int L128 = 32 * q + lane;               // output column inside the 128-column block = TMEM lane
+    const int tsel = L128 >> 4, row = L128 & 15;  // which of the block's 8 tiles, row inside it
+    const uint32_t lane_base = static_cast<uint32_t>(32 * q) << 16;
+    const uint32_t rot = scratch + wi * p.rot_bytes;
+    DEC_TRACE(2);
+    pdl_wait();  // x may have been written by the previous kernel
+    DEC_TRACE(3);
+    {
+      const int M = p.M;
+      if (M == 1) dec_prologue<T, 1>(p, rm, part, g_begin, ng, wi, kWorkers, lane, rot, xb, t_entry);
+      else if (M == 2) dec_prologue<T, 2>(p, rm, part, g_begin, ng, wi, kWorkers, lane, rot, xb, t_entry);
+      else if (M <= 4) dec_prologue<T, 4>(p, rm, part, g_begin, ng, wi, kWorkers, lane, rot, xb, t_entry);
+      else if (M <= 8) dec_prologue<T, 8>(p, rm, part, g_begin, ng, wi, kWorkers, lane, rot, xb, t_entry);
+      else dec_prologue<T, 16>(p, rm, part, g_begin, ng, wi, kWorkers, lane, rot, xb, t_entry);
+    }
+    fence_proxy_async_smem();  // B rows were written through the generic proxy, tcgen05.mma reads them through the async proxy
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_xb);
+    // the rotation tiles are dead from here on: peers may now use the same bytes as my DSMEM receive buffer
+    if (p.c > 1) cluster_arrive_release();  // #1 -- waited on before the first DSMEM push
+    DEC_TRACE(4);
+
+    const int M = p.M;
+    // scale / zero of (my column, group): small and L2-resident, read straight from the packed records one
+    // of this set's rounds ahead so the latency never sits in front of the dequant
+    const uint32_t qp_row = static_cast<uint32_t>(p.gps) * kUnitWeightBytes + row * 2;
+    const uint32_t zp_row = static_cast<uint32_t>(p.gps) * (kUnitWeightBytes + 32) + row;
+    auto fetch_qparam = [&](int j, int gi, bool ok, uint32_t &sbits, uint32_t &z) {
+      sbits = 0; z = 0;
+      if (ok) {
+        const int g = g_begin + gi, ls = g >> p.gps_shift, u = g & (p.gps - 1);
+        const uint8_t *rec = rec_part + (static_cast<size_t>(ls) * tp + (cb_begin + j) * 8 + tsel) * p.rec_bytes;
+        sbits = __ldg(reinterpret_cast<const uint16_t *>(rec + qp_row + u * 32));
+        z = __ldg(rec + zp_row + u * 16);
+      }
+    };
+
+    int j = 0, gi = e;
+    while (gi >= ng && j < nj) { gi -= ng; ++j; }
+    int st = e, use = 0;
+    uint32_t par = 0;
+    uint32_t sbits, z;
+    fetch_qparam(j, gi, e < nrounds, sbits, z);
+    const uint32_t ta = tmem + lane_base + e * 64;
+    const uint32_t unit_off = tsel * kUnitWeightBytes + row * 16;
+    bool first = true;
+#pragma unroll 1
+    for (int r = e; r < nrounds; r += SETS) {
+      int gi2 = gi + SETS, j2 = j;
+      while (gi2 >= ng) { gi2 -= ng; ++j2; }
+      uint32_t sbits_next, z_next;
+      fetch_qparam(j2, gi2, r + SETS < nrounds, sbits_next, z_next);
+      mbar_wait(bar_wfull + 8 * st, par);
+      if (first) { DEC_TRACE(5); first = false; }
+      if (p.trace && q == 0 && lane == 0 && blockIdx.x == 0 && r < 100) g_dec_trace[200 * kDecTraceSlots + 3 * r + 1] = clock64() - t_entry;
+      if (use > 0) mbar_wait(bar_afree + 8 * e, (use - 1) & 1);  // the MMAs of my previous round have drained my A buffer
+      tc_fence_after();
+      RowDequant<T> dq;
+      dq.prep(sbits, z);
+      const uint32_t wbase = smem0 + st * 8192 + unit_off;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint4 w4 = lds128(wbase + c * 256);
+        uint32_t regs[16];
+        dq.word(w4.x, regs + 0);
+        dq.word(w4.y, regs + 4);
+        dq.word(w4.z, regs + 8);
+        dq.word(w4.w, regs + 12);
+        tc_st16(ta + 16 * c, regs);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_afull + 8 * e);
+        mbar_arrive(bar_wempty + 8 * st);
+        if (p.trace && q == 0 && blockIdx.x == 0 && r < 100) g_dec_trace[200 * kDecTraceSlots + 3 * r + 2] = clock64() - t_entry;
+      }
+      if (gi == ng - 1) {
+        // ---- this set closed block j: read D back, one value per token
+        const int b = j & 1;
+        mbar_wait(bar_dfull + 8 * b, (j >> 1) & 1);
+        tc_fence_after();
+        uint32_t v[16];
+        {
+          const uint32_t td = tmem + lane_base + d_col0 + b * (p.nacc * kDecN);
+          if (M <= 8) tc_ld8(td, v);
+          else tc_ld16(td, v);
+          tc_wait_ld();
+          for (int a = 1; a < p.nacc; ++a) {
+            uint32_t w[16];
+            if (M <= 8) tc_ld8(td + a * kDecN, w);
+            else tc_ld16(td + a * kDecN, w);
+            tc_wait_ld();
+#pragma unroll
+            for (int m = 0; m < 16; ++m)
+              if (m < 8 || M > 8) v[m] = __float_as_uint(__uint_as_float(v[m]) + __uint_as_float(w[m]));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dfree + 8 * b);
+        if (p.c == 1) {
+          const int n = (p.part_tile_begin[part] + (cb_begin + j) * 8) * kTileN + L128;
+#pragma unroll
+          for (int m = 0; m < 16; ++m)
+            if (m < M) dec_store<T>(p, __uint_as_float(v[m]), m, n);
+        } else {
+          if (!cluster_ready) { cluster_wait_acquire(); cluster_ready = true; }  // #1: every peer is past its prologue
+          const uint32_t dst = map_to_rank(scratch + (((j >> p.c_shift) << p.c_shift) + slice) * (M * 512) + L128 * 4, j & (p.c - 1));
+#pragma unroll
+          for (int m = 0; m < 16; ++m)
+            if (m < M) st_cluster_f32(dst + m * 512, __uint_as_float(v[m]));
+        }
+      }
+      st += SETS;
+      if (st >= NS) { st -= NS; par ^= 1; }
+      ++use;
+      gi = gi2; j = j2;
+      sbits = sbits_next; z = z_next;
+    }
+    DEC_TRACE(6);
+  }
+
+  // ================= common tail (all threads; warps reconverge first)
+  __syncwarp();
+  if (p.c > 1) {
+    if (!cluster_ready) cluster_wait_acquire();
+    cluster_arrive_release();                              // #2: all my pushes are done
+    cluster_wait_acquire();
+    DEC_TRACE(7);
+    if (warp < kWorkers) {
+      // finish the blocks that were sent to me (j % c == slice); fixed order over the K-slices
+      const int M = p.M;
+      const int nmine = nj > slice ? ((nj - slice + p.c - 1) >> p.c_shift) : 0;
+      const int per = M * 128;
+      for (int idx = threadIdx.x; idx < nmine * per; idx += 32 * kWorkers) {
+        const int jo = idx / per, o = idx - jo * per;
+        const int m = o >> 7, col = o & 127;
+        float acc = 0.f;
+        for (int src = 0; src < p.c; ++src) acc += lds_f32(scratch + ((jo << p.c_shift) + src) * (M * 512) + o * 4);
+        const int j = (jo << p.c_shift) + slice;
+        dec_store<T>(p, acc, m, (p.part_tile_begin[part] + (cb_begin + j) * 8) * kTileN + col);
+      }
+    }
+  }
+  DEC_TRACE(8);
+  if (p.trace && threadIdx.x == 0 && blockIdx.x < 200) g_dec_trace[blockIdx.x * kDecTraceSlots + 11] = globaltimer_ns();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWorkers + 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kDecTmemCols) : "memory");
+  }
+}
+
+int decode2_trace_read(unsigned long long *host, int max_ctas) {
+  const size_t n = static_cast<size_t>(max_ctas < kDecTraceMaxCtas ? max_ctas : kDecTraceMaxCtas) * kDecTraceSlots;
+  PARO_CUDA_OK(cudaMemcpyFromSymbol(host, g_dec_trace, n * sizeof(unsigned long long)));
+  return PARO_OK;
+}
+
+// ------------------------------------------------------------------ host side
+static int dec_env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+struct DecPlan {
+  int c, c_shift, ranges, grid;
+  int part_range_begin[PARO_MAX_PARTS + 1];
+  int nj_max, ng_max;
+};
+
+// `ranges` block ranges over the partitions, proportional to their 128-column block counts (largest remainder)
+static bool dec_split_ranges(const Layout &L, int ranges, DecPlan &plan) {
+  int cb[PARO_MAX_PARTS], alloc[PARO_MAX_PARTS], total = 0;
+  double frac[PARO_MAX_PARTS];
+  for (int p = 0; p < L.n_parts; ++p) {
+    cb[p] = (L.part_tile_begin[p + 1] - L.part_tile_begin[p]) / 8;
+    total += cb[p];
+  }
+  if (ranges > total) ranges = total;
+  if (ranges < L.n_parts) return false;
+  int used = 0;
+  for (int p = 0; p < L.n_parts; ++p) {
+    const double exact = static_cast<double>(ranges) * cb[p] / total;
+    alloc[p] = static_cast<int>(exact);
+    if (alloc[p] < 1) alloc[p] = 1;
+    if (alloc[p] > cb[p]) alloc[p] = cb[p];
+    frac[p] = exact - alloc[p];
+    used += alloc[p];
+  }
+  while (used < ranges) {
+    int best = -1;
+    for (int p = 0; p < L.n_parts; ++p)
+      if (alloc[p] < cb[p] && (best < 0 || frac[p] > frac[best])) best = p;
+    if (best < 0) break;
+    alloc[best]++; frac[best] -= 1.0; used++;
+  }
+  while (used > ranges) {
+    int best = -1;
+    for (int p = 0; p < L.n_parts; ++p)
+      if (alloc[p] > 1 && (best < 0 || frac[p] < frac[best])) best = p;
+    if (best < 0) return false;
+    alloc[best]--; frac[best] += 1.0; used--;
+  }
+  plan.part_range_begin[0] = 0;
+  plan.nj_max = 0;
+  for (int p = 0; p < PARO_MAX_PARTS; ++p) {
+    plan.part_range_begin[p + 1] = plan.part_range_begin[p] + (p < L.n_parts ? alloc[p] : 0);
+    if (p < L.n_parts) {
+      const int mx = (cb[p] + alloc[p] - 1) / alloc[p];
+      if (mx > plan.nj_max) plan.nj_max = mx;
+    }
+  }
+  plan.ranges = plan.part_range_begin[L.n_parts];
+  return plan.ranges > 0;
+}
+
+bool decode2_supported(const Layout &L, int64_t M) {
+  if (M < 1 || M > 16) return false;
+  if (dec_env_int("PARO_DECODE_V1", 0)) return false;
+  for (int p = 0; p < L.n_parts; ++p)
+    if ((L.part_tile_begin[p + 1] - L.part_tile_begin[p]) % 8) return false;   // partitions of whole 128-column blocks
+  return true;
+}
+
+struct DecSmem { int xb_off, scratch_off, bar_off, nstages, total; };
+
+static bool dec_carve(const DecPlan &plan, int M, int rot_bytes, int sets, DecSmem &s) {
+  const int xb_bytes = plan.ng_max * kDecN * 256;
+  const int rot_total = 4 * sets * rot_bytes;
+  const int recv = plan.c > 1 ? ((plan.nj_max + plan.c - 1) / plan.c) * plan.c * M * 512 : 0;
+  const int scr = rot_total > recv ? rot_total : recv;
+  const int bar_bytes = 16 * kDecMaxStages + 256;
+  const int fixed = xb_bytes + (scr + 127) / 128 * 128 + bar_bytes;
+  int nst = (kDecSmemLimit - fixed) / 8192;
+  if (nst > kDecMaxStages) nst = kDecMaxStages;
+  const int want = dec_env_int("PARO_DECODE_STAGES", 0);
+  if (want >= sets && want < nst) nst = want;
+  if (nst < sets + 2) return false;
+  s.nstages = nst;
+  s.xb_off = nst * 8192;
+  s.scratch_off = s.xb_off + xb_bytes;
+  s.bar_off = s.scratch_off + (scr + 127) / 128 * 128;
+  s.total = s.bar_off + bar_bytes;
+  return true;
+}
+
+// how many clusters of `c` CTAs with this footprint the device keeps resident (GPC granularity); cached per thread
+template <typename T, int SETS>
+static int max_resident_clusters(int c, int smem_bytes, int sms) {
+  if (c == 1) return sms;
+  thread_local int cached_smem[4] = {0, 0, 0, 0}, cached_val[4] = {0, 0, 0, 0};
+  int slot = 0;
+  while ((1 << slot) < c) ++slot;
+  if (cached_smem[slot] == smem_bytes && cached_val[slot] > 0) return cached_val[slot];
+  auto kern = decode_kernel<T, SETS>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((sms / c) * c);
+  cfg.blockDim = dim3(32 * (4 * SETS + 2));
+  cfg.dynamicSmemBytes = smem_bytes;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = c;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+  cached_smem[slot] = smem_bytes;
+  cached_val[slot] = n;
+  return n;
+}
+
+template <typename T, int SETS>
+static int launch_decode2(DecParams &p, const Layout &L, int sms, cudaStream_t stream) {
+  auto kern = decode_kernel<T, SETS>;
+  const bool cluster_ok = !dec_env_int("PARO_NO_CLUSTER", 0);
+  const int force_c = dec_env_int("PARO_DECODE_C", 0);
+  DecPlan best = {};
+  DecSmem best_s = {};
+  long best_cost = -1;
+  for (int cs = 0; cs <= 3; ++cs) {
+    const int c = 1 << cs;
+    if (c > 1 && !cluster_ok) break;
+    if (c > L.groups) break;
+    if (force_c && c != force_c) continue;
+    DecPlan plan = {};
+    plan.c = c; plan.c_shift = cs;
+    plan.ng_max = (L.groups + c - 1) / c;
+    if (!dec_split_ranges(L, sms / c, plan)) continue;
+    DecSmem s;
+    if (!dec_carve(plan, p.M, p.rot_bytes, SETS, s)) continue;
+    // all clusters must be co-resident (one wave): the device may hold fewer clusters than sms / c
+    const int resident = max_resident_clusters<T, SETS>(c, s.total, sms);
+    if (resident < L.n_parts) continue;
+    if (resident < plan.ranges) {
+      if (!dec_split_ranges(L, resident, plan)) continue;
+      if (!dec_carve(plan, p.M, p.rot_bytes, SETS, s)) continue;
+    }
+    plan.grid = plan.ranges * c;
+    // critical path in rounds: main loop of the busiest CTA + rotation passes + a small charge per doubling of the cluster
+    const int passes = (plan.ng_max + 4 * SETS - 1) / (4 * SETS);
+    const long cost = static_cast<long>(plan.nj_max) * plan.ng_max * 8 + passes * 24 + cs * 2;
+    if (best_cost < 0 || cost < best_cost) { best = plan; best_s = s; best_cost = cost; }
+  }
+  if (best_cost < 0) { set_error("decode: no launch configuration fits (in_features=%d, M=%d)", L.K, p.M); return PARO_EUNSUPPORTED; }
+  if (dec_env_int("PARO_DECODE_VERBOSE", 0))
+    fprintf(stderr, "[paro decode] K=%d N=%d M=%d: cluster %d x %d ranges (grid %d), blocks/CTA <= %d, groups/CTA <= %d, %d stages, smem %d\n",
+            L.K, L.N, p.M, best.c, best.ranges, best.grid, best.nj_max, best.ng_max, best_s.nstages, best_s.total);
+
+  PARO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, best_s.total));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(best.grid);
+  cfg.blockDim = dim3(32 * (4 * SETS + 2));
+  cfg.dynamicSmemBytes = best_s.total;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (best.c > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = best.c;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (!dec_env_int("PARO_NO_PDL", 0)) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  p.c = best.c; p.c_shift = best.c_shift;
+  p.nstages = best_s.nstages;
+  p.xb_off = best_s.xb_off; p.scratch_off = best_s.scratch_off; p.bar_off = best_s.bar_off;
+  for (int i = 0; i <= PARO_MAX_PARTS; ++i) p.part_range_begin[i] = best.part_range_begin[i];
+  PARO_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
+  note_launches(1);
+  return PARO_OK;
+}
+
+int decode2_forward(const paro_linear_shape &s, const Layout &L, const void *packed, const void *x, int64_t M,
+                    const void *bias, void *y, cudaStream_t stream) {
+  int dev = 0, sms = 0;
+  PARO_CUDA_OK(cudaGetDevice(&dev));
+  PARO_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  DecParams p = {};
+  p.packed = static_cast<const uint8_t *>(packed);
+  p.x = x; p.y = y; p.bias = bias;
+  p.M = static_cast<int>(M); p.K = L.K; p.N = L.N;
+  p.n_parts = L.n_parts; p.groups = L.groups; p.krot = L.krot;
+  p.gps = L.gps; p.gps_shift = L.gps == 16 ? 4 : 3; p.lslices = L.slices; p.rec_bytes = L.rec_bytes;
+  p.rot_bytes = kGroup * 2 * (M == 1 ? 1 : M == 2 ? 2 : M <= 4 ? 4 : M <= 8 ? 8 : 16);
+  p.trace = dec_env_int("PARO_DECODE_TRACE", 0);
+  p.fake1 = dec_env_int("PARO_DECODE_FAKE1", 0);
+  for (int i = 0; i <= PARO_MAX_PARTS; ++i) p.part_tile_begin[i] = L.part_tile_begin[i];
+  p.meta_group_bytes = L.meta_group_bytes;
+  p.meta_off = static_cast<long long>(L.meta_off);
+  p.rec_off = static_cast<long long>(L.rec_off);
+  const int sets = dec_env_int("PARO_DECODE_SETS", 6);
+  // TMEM: sets x 64 columns of A + 2 D buffers x nacc accumulators x 16 columns
+  int nacc = dec_env_int("PARO_DECODE_NACC", 4);
+  nacc = nacc >= 8 ? 8 : nacc >= 4 ? 4 : nacc >= 2 ? 2 : 1;
+  while (64 * (sets == 5 || sets == 7 || sets == 4 ? sets : 6) + 2 * nacc * kDecN > kDecTmemCols) nacc >>= 1;
+  p.nacc = nacc;
+  const bool bf16 = s.dtype == PARO_BF16;
+  switch (sets) {
+    case 4: return bf16 ? launch_decode2<__nv_bfloat16, 4>(p, L, sms, stream) : launch_decode2<__half, 4>(p, L, sms, stream);
+    case 5: return bf16 ? launch_decode2<__nv_bfloat16, 5>(p, L, sms, stream) : launch_decode2<__half, 5>(p, L, sms, stream);
+    case 7: return bf16 ? launch_decode2<__nv_bfloat16, 7>(p, L, sms, stream) : launch_decode2<__half, 7>(p, L, sms, stream);
+    default: return bf16 ? launch_decode2<__nv_bfloat16, 6>(p, L, sms, stream) : launch_decode2<__half, 6>(p, L, sms, stream);
+  }
+}
+
+}  // namespace paro

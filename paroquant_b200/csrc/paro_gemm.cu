@@ -84,6 +84,11 @@ template <typename T> __device__ __forceinline__ uint32_t g_instr_desc(int n) {
   const uint32_t fmt = Traits<T>::code == PARO_BF16 ? 1u : 0u;
   return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (8u << 24);
 }
+__device__ __forceinline__ bool g_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t g_and_or(uint32_t a, uint32_t mask, uint32_t magic) {
   uint32_t d;
   asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(mask), "r"(magic));
@@ -205,10 +210,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const GemmPara
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer
-    if (lane == 0) {
+    // ================= MMA issuer: the whole warp runs the loop, ONE elected lane issues (inside an elect.sync
+    // region ptxas keeps descriptors in uniform registers; a plain `lane == 0` branch wraps every tcgen05.mma
+    // in a divergence loop and the issuing thread, not the tensor pipe, becomes the limit at small NT)
+    {
       const uint32_t idesc = g_instr_desc<T>(NT);
       const uint32_t step_bytes = NT * 32, lbo = NT * 16;
+      const uint64_t desc_hi = g_desc_kmajor(0, lbo, 128);
       int abuf = 0, a_use = 0;
       for (int r = 0; r < rounds; ++r) {
         mbar_wait(bar_afull + 8 * abuf, a_use & 1);
@@ -216,18 +224,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const GemmPara
           const int bi = 2 * r + hstage, bs = bi % kBStages;
           mbar_wait(bar_bfull + 8 * bs, (bi / kBStages) & 1);
           g_fence_after();
+          const uint64_t bdesc0 = desc_hi | static_cast<uint64_t>(((b_ring + bs * b_stage_bytes) >> 4) & 0x3FFF);
+          if (g_elect_one()) {
 #pragma unroll
-          for (int s4 = 0; s4 < 4; ++s4) {
-            const int s = hstage * 4 + s4;
-            g_mma_ts(tmem + d_col0, tmem + abuf * 64 + 8 * s, g_desc_kmajor(b_ring + bs * b_stage_bytes + s4 * step_bytes, lbo, 128), idesc,
-                     (r | s) ? 1u : 0u);
+            for (int s4 = 0; s4 < 4; ++s4) {
+              const int s = hstage * 4 + s4;
+              g_mma_ts(tmem + d_col0, tmem + abuf * 64 + 8 * s, bdesc0 + s4 * (step_bytes >> 4), idesc, (r | s) ? 1u : 0u);
+            }
+            g_commit(bar_bempty + 8 * bs);
+            if (hstage == 1) {
+              g_commit(bar_afree + 8 * abuf);
+              if (r == rounds - 1) g_commit(bar_dfull);
+            }
           }
-          g_commit(bar_bempty + 8 * bs);
+          __syncwarp();
         }
-        g_commit(bar_afree + 8 * abuf);
         if (++abuf == kABufs) { abuf = 0; ++a_use; }
       }
-      g_commit(bar_dfull);
     }
   } else {
     // ================= workers: thread = one output column (TMEM lane)
