@@ -45,6 +45,22 @@ SHAPES = {  # name: (K, part_sizes, kind)
 }
 
 
+def traffic_from_profile():
+    """DRAM bytes (read + write) of ONE launch of the dominant kernel, from the committed `ncu --set full` summary
+    (profiles/r01_decode_gate_up_m1_ncu.txt: the gate_up launch, 61.29 MB algorithmic).  None if the file is absent."""
+    f = ROOT / "profiles" / "r01_decode_gate_up_m1_ncu.txt"
+    if not f.exists():
+        return None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for ln in f.read_text().splitlines():
+        t = ln.split()
+        if len(t) >= 3 and t[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and t[2] in unit:
+            tot += float(t[1].replace(",", "")) * unit[t[2]]
+    return {"bytes_per_launch": tot, "launch": "gate_up 4096->28672 M=1", "algorithmic_bytes": algorithmic_bytes(4096, [14336, 14336], 1),
+            "source": "profiles/r01_decode_gate_up_m1_ncu.txt"} if tot else None
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -237,7 +253,7 @@ def run_ours(args):
             "gpu_launches": launches_per_step * args.steps,
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": src, "kernel": "paro::decode_kernel", "launches_per_step": launches_per_step,
+                         "traffic": traffic_from_profile(), "peak_source": src, "kernel": "paro::decode_kernel", "launches_per_step": launches_per_step,
                          "algorithmic_bytes_per_step": step_bytes, "avg_launch_us": ms * 1e3 / max(launches_per_step, 1)},
         }
         if world == 1 and not args.no_prefill:

@@ -28,19 +28,14 @@ int prepack_launch(const paro_linear_shape &s, const Layout &L, const int32_t *q
                    const void *scales, int scales_dtype, const int16_t *pairs, const void *theta, int theta_dtype,
                    const void *cscales, int cs_dtype, void *packed, cudaStream_t stream);
 int unpack_dense_launch(const paro_linear_shape &s, const Layout &L, const void *packed, void *W, cudaStream_t stream);
-size_t decode_workspace_bytes(const Layout &L, int64_t max_m);
+bool decode_supported(const Layout &L, int64_t M);
 int decode_forward(const paro_linear_shape &s, const Layout &L, const void *packed, const void *x, int64_t M,
-                   const void *bias, void *y, void *workspace, size_t workspace_bytes, cudaStream_t stream);
-bool decode2_supported(const Layout &L, int64_t M);
-int decode2_forward(const paro_linear_shape &s, const Layout &L, const void *packed, const void *x, int64_t M,
-                    const void *bias, void *y, cudaStream_t stream);
-int decode2_trace_read(unsigned long long *host, int max_ctas);
+                   const void *bias, void *y, cudaStream_t stream);
+int decode_trace_read(unsigned long long *host, int max_ctas);
 size_t gemm_workspace_bytes(const Layout &L, int64_t max_m);
-int debug_trace_read(unsigned long long *host, int max_ctas);
 int gemm_forward(const paro_linear_shape &s, const Layout &L, const void *packed, const void *x, int64_t M,
                  const void *bias, void *y, void *workspace, size_t workspace_bytes, cudaStream_t stream);
 
-static thread_local bool g_last_small_v2 = false;
 static bool valid_dtype(int d) { return d == PARO_F32 || d == PARO_F16 || d == PARO_BF16; }
 static bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
@@ -98,9 +93,9 @@ size_t paro_workspace_bytes(const paro_linear_shape *shape, int64_t max_m) {
   Layout L;
   const char *why = "";
   if (!shape || !make_layout(*shape, L, &why)) { set_error("workspace_bytes: %s", shape ? why : "null shape"); return 0; }
-  const size_t a = decode_workspace_bytes(L, max_m < 16 ? max_m : 16);
+  // the small-M kernel reduces through distributed shared memory and needs no global scratch; M > 16 stages x_rot
   const size_t b = max_m > 16 ? gemm_workspace_bytes(L, max_m) : 0;
-  return a > b ? a : b;
+  return b > 256 ? b : 256;
 }
 
 int paro_linear_forward(const paro_linear_shape *shape, const void *packed, const void *x, int64_t M, const void *bias,
@@ -117,12 +112,7 @@ int paro_linear_forward(const paro_linear_shape *shape, const void *packed, cons
     return PARO_EINVAL;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (M <= 16) {
-    // one persistent CTA per SM (paro_decode.cu); partitions that are not whole 128-column blocks take the 16-column-tile kernel
-    g_last_small_v2 = decode2_supported(L, M);
-    if (g_last_small_v2) return decode2_forward(*shape, L, packed, x, M, bias, y, st);
-    return decode_forward(*shape, L, packed, x, M, bias, y, workspace, workspace_bytes, st);
-  }
+  if (M <= 16) return decode_forward(*shape, L, packed, x, M, bias, y, st);   // one persistent CTA per SM (paro_decode.cu)
   return gemm_forward(*shape, L, packed, x, M, bias, y, workspace, workspace_bytes, st);
 }
 
@@ -137,7 +127,7 @@ int paro_unpack_dense(const paro_linear_shape *shape, const void *packed, void *
 
 int paro_debug_trace(unsigned long long *host_out, int32_t max_ctas) {
   if (!host_out || max_ctas <= 0) { set_error("debug_trace: bad arguments"); return PARO_EINVAL; }
-  return g_last_small_v2 ? decode2_trace_read(host_out, max_ctas) : debug_trace_read(host_out, max_ctas);
+  return decode_trace_read(host_out, max_ctas);
 }
 
 }  // extern "C"

@@ -19,8 +19,9 @@
 // Roles (SETS x 4 dequant warps + 2): warps 0..4*SETS-1 workers (TMEM lane quarter = warp % 4): the
 // prologue rotates the slice's groups (one group per warp, __syncwarp only); the main loop takes rounds
 // r = set, set + SETS, ...; the set that dequantised a block's last group reads D back.  Warp 4*SETS:
-// TMA producer (8 x 1 KB unit copies per round into an mbarrier ring, issued before
-// griddepcontrol.wait).  Warp 4*SETS+1: TMEM allocator + single-thread tcgen05.mma issuer.
+// TMA producer (ONE 8576-byte record = weights + scales + zeros of a round per cp.async.bulk, into an
+// mbarrier ring, issued before griddepcontrol.wait).  Warp 4*SETS+1: TMEM allocator + tcgen05.mma issuer
+// (one elected lane).
 //
 // Numerics: x_rot as paro_rotate.cu; W = T((q - z) * T(s)) with ONE rounding (the operand Marlin / AWQ
 // form); fp32 accumulation in TMEM; one rounding to T; bias added in T (plugin.py:309-310).
@@ -34,13 +35,15 @@ constexpr int kDecMaxStages = 24;
 constexpr int kDecTmemCols = 512;
 constexpr int kDecN = 16;            // MMA N: token rows, zero-padded (M_mma = 128 needs N % 16 == 0)
 constexpr int kDecSmemLimit = 227 * 1024;
+constexpr int kDecStage = kBlockBytes;   // one record per ring stage (8576 bytes, a multiple of 64)
 
 constexpr int kDecTraceSlots = 12;
-constexpr int kDecTraceMaxCtas = 256;   // rows 200.. double as a per-round log of CTA 0 (issue / full / consumed)
-__device__ unsigned long long g_dec_trace[kDecTraceMaxCtas * kDecTraceSlots];
+constexpr int kDecTraceCtas = 200;       // rows 200.. of the trace double as a per-round log of CTA 0 (issued / full / consumed)
+constexpr int kDecTraceRows = 256;
+__device__ unsigned long long g_dec_trace[kDecTraceRows * kDecTraceSlots];
 #define DEC_TRACE(slot)                                                                                      \
   do {                                                                                                       \
-    if (p.trace && warp == 0 && lane == 0 && blockIdx.x < 200)                                   \
+    if (p.trace && warp == 0 && lane == 0 && blockIdx.x < kDecTraceCtas)                                      \
       g_dec_trace[blockIdx.x * kDecTraceSlots + (slot)] = static_cast<unsigned long long>(clock64() - t_entry); \
   } while (0)
 
@@ -50,12 +53,12 @@ struct DecParams {
   void *y;
   const void *bias;
   int M, K, N;
-  int n_parts, groups, krot, gps, gps_shift, lslices, rec_bytes;
+  int n_parts, groups, krot;
   int c, c_shift;                 // cluster size (K slices of this launch), log2
-  int nstages, rot_bytes, trace;
-  int nacc, fake1;                // independent accumulators per D buffer (k16 step s -> accumulator s % nacc); experiment switch
-  int xb_off, scratch_off, bar_off;   // shared-memory carve-up (bytes); scratch = rotation tiles, later the DSMEM receive buffer
-  int part_tile_begin[PARO_MAX_PARTS + 1];
+  int nstages, rot_bytes, rot_warps, trace;   // rot_warps: worker warps that rotate (one group each per pass)
+  int xb_off, rot_off, recv_off, bar_off;   // shared-memory carve-up (bytes)
+  int part_col_begin[PARO_MAX_PARTS + 1];
+  int part_block_begin[PARO_MAX_PARTS + 1];
   int part_range_begin[PARO_MAX_PARTS + 1];
   int meta_group_bytes;
   long long meta_off, rec_off;
@@ -123,7 +126,7 @@ __device__ __forceinline__ void dec_rotate_group(const DecParams &p, const DecRo
   load_x<T, ROWS>(p, gk, lane, raw);
   scale_and_stage<T, ROWS>(rot, lane, raw, rm.csw);
   __syncwarp();
-  if (p.trace && threadIdx.x == 0 && blockIdx.x < 200) g_dec_trace[blockIdx.x * kDecTraceSlots + 0] = clock64() - t_entry;
+  if (p.trace && threadIdx.x == 0 && blockIdx.x < kDecTraceCtas) g_dec_trace[blockIdx.x * kDecTraceSlots + 0] = clock64() - t_entry;
   if (p.krot == 8) {
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
@@ -143,7 +146,7 @@ __device__ __forceinline__ void dec_rotate_group(const DecParams &p, const DecRo
       __syncwarp();
     }
   }
-  if (p.trace && threadIdx.x == 0 && blockIdx.x < 200) g_dec_trace[blockIdx.x * kDecTraceSlots + 9] = clock64() - t_entry;
+  if (p.trace && threadIdx.x == 0 && blockIdx.x < kDecTraceCtas) g_dec_trace[blockIdx.x * kDecTraceSlots + 9] = clock64() - t_entry;
   dec_write_b_rows<T, ROWS>(xb_group, rot, p.M, lane);
   __syncwarp();
 }
@@ -170,13 +173,13 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
   constexpr int kWorkers = 4 * SETS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long t_entry = clock64();
-  if (p.trace && threadIdx.x == 0 && blockIdx.x < 200) g_dec_trace[blockIdx.x * kDecTraceSlots + 10] = globaltimer_ns();
+  if (p.trace && threadIdx.x == 0 && blockIdx.x < kDecTraceCtas) g_dec_trace[blockIdx.x * kDecTraceSlots + 10] = globaltimer_ns();
   const int NS = p.nstages;
   const uint32_t smem0 = smem_u32(smem);
-  const uint32_t xb = smem0 + p.xb_off, scratch = smem0 + p.scratch_off, bars = smem0 + p.bar_off;
+  const uint32_t xb = smem0 + p.xb_off, recv = smem0 + p.recv_off, bars = smem0 + p.bar_off;
   const uint32_t bar_wfull = bars, bar_wempty = bars + 8 * kDecMaxStages;
   const uint32_t bar_afull = bars + 16 * kDecMaxStages, bar_afree = bar_afull + 64;
-  const uint32_t bar_dfull = bar_afull + 128, bar_dfree = bar_afull + 144, bar_xb = bar_afull + 160, tmem_slot = bar_afull + 168;
+  const uint32_t bar_dfull = bar_afull + 128, bar_dfree = bar_afull + 192, bar_xb = bar_afull + 208, tmem_slot = bar_afull + 216;
   constexpr uint32_t d_col0 = 64 * SETS;
 
   // ---- my range of 128-column blocks (within one partition) and my K-slice (whole groups, ragged)
@@ -186,8 +189,7 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
   while (range >= p.part_range_begin[part + 1]) ++part;
   const int jl = range - p.part_range_begin[part];
   const int cp = p.part_range_begin[part + 1] - p.part_range_begin[part];
-  const int tp = p.part_tile_begin[part + 1] - p.part_tile_begin[part];
-  const int cbp = tp >> 3;
+  const int cbp = p.part_block_begin[part + 1] - p.part_block_begin[part];
   const int cb_begin = static_cast<int>(static_cast<unsigned>(jl) * static_cast<unsigned>(cbp) / static_cast<unsigned>(cp));
   const int cb_end = static_cast<int>(static_cast<unsigned>(jl + 1) * static_cast<unsigned>(cbp) / static_cast<unsigned>(cp));
   const int nj = cb_end - cb_begin;
@@ -195,8 +197,10 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
   const int g_end = static_cast<int>(static_cast<unsigned>(slice + 1) * static_cast<unsigned>(p.groups) >> p.c_shift);
   const int ng = g_end - g_begin;
   const int nrounds = nj * ng;
-  // records of this partition: (L-slice, tile) -> rec_part + (lslice * tp + tile_in_part) * rec_bytes
-  const uint8_t *rec_part = p.packed + p.rec_off + static_cast<size_t>(p.lslices) * p.part_tile_begin[part] * p.rec_bytes;
+  // first output column of my first block, and the end of my partition (a last partial block is masked at the stores)
+  const int n_first = p.part_col_begin[part] + cb_begin * kBlockN, n_end = p.part_col_begin[part + 1];
+  // record of (block j, group gi) of mine: rec0 + (j * groups + gi) * kBlockBytes
+  const uint8_t *rec0 = p.packed + p.rec_off + (static_cast<size_t>(p.part_block_begin[part] + cb_begin) * p.groups + g_begin) * kBlockBytes;
 
   DecRotMeta rm;
   if (warp < kWorkers && warp < ng) dec_fetch_meta(p, part, g_begin + warp, lane, rm);   // flies during the barrier init / TMEM allocation
@@ -207,14 +211,15 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
       mbar_init(bar_wfull + 8 * lane, 1);
       mbar_init(bar_wempty + 8 * lane, 4);
     }
+    // Every barrier has ONE waiting party that consumes its phases in order (a parity wait issued a phase early passes
+    // on the stale phase): A-buffer and D-ready barriers are per dequant set, ring stages are always consumed by the
+    // same set (stage count is a multiple of SETS), the producer / MMA lanes wait sequentially on the rest.
     if (lane < SETS) {
       mbar_init(bar_afull + 8 * lane, 4);
       mbar_init(bar_afree + 8 * lane, 1);
-    }
-    if (lane < 2) {
       mbar_init(bar_dfull + 8 * lane, 1);
-      mbar_init(bar_dfree + 8 * lane, 4);
     }
+    if (lane < 2) mbar_init(bar_dfree + 8 * lane, 4);
     if (lane == 0) mbar_init(bar_xb, kWorkers);
     fence_mbar_init();
   }
@@ -227,27 +232,24 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
   tc_fence_after();
   const uint32_t tmem = lds32(tmem_slot);
   DEC_TRACE(1);
-  pdl_launch_dependents();   // let the next linear in the stream start prefetching its weights
+  if (p.c > 1) cluster_arrive_relaxed();   // #1 "this CTA runs" -- waited on before the first DSMEM push into a peer's receive buffer
+  pdl_launch_dependents();                 // let the next linear in the stream start prefetching its weights
   bool cluster_ready = false;
 
   if (warp == kWorkers) {
-    // ================= producer: 8 unit copies per round, one per lane; nothing here depends on the previous kernel
-    if (p.c > 1) cluster_arrive_release();   // #1 (the workers arrive once their rotation tiles are dead)
+    // ================= producer: ONE bulk copy per round (weights + scales + zeros of a (block, group), 8576 contiguous
+    // bytes); nothing here depends on the previous kernel.  The whole warp runs the loop, an elected lane issues.
     const uint64_t pol = policy_evict_first();
     int st = 0, it = 0, j = 0, gi = 0;
+#pragma unroll 1
     for (int r = 0; r < nrounds; ++r) {
-      if (lane < 8) {
-        if (it > 0) mbar_wait(bar_wempty + 8 * st, (it - 1) & 1);
-        const int g = g_begin + gi, ls = g >> p.gps_shift, u = g & (p.gps - 1);
-        const uint8_t *src = rec_part + (static_cast<size_t>(ls) * tp + (cb_begin + j) * 8 + lane) * p.rec_bytes + u * kUnitWeightBytes;
-        if (lane == 0) mbar_arrive_expect_tx(bar_wfull + 8 * st, 8 * kUnitWeightBytes);
-        if (p.trace && lane == 0 && blockIdx.x == 0 && r < 100) g_dec_trace[200 * kDecTraceSlots + 3 * r] = clock64() - t_entry;
-        if (p.fake1) {   // timing experiment only (wrong data): one 8 KB copy per round
-          if (lane == 0) bulk_g2s(smem0 + st * 8192, rec_part + static_cast<size_t>(cb_begin * ng + r) * 8192, 8192, bar_wfull + 8 * st, pol);
-        } else {
-          bulk_g2s(smem0 + st * 8192 + lane * kUnitWeightBytes, src, kUnitWeightBytes, bar_wfull + 8 * st, pol);
-        }
+      if (it > 0) mbar_wait(bar_wempty + 8 * st, (it - 1) & 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar_wfull + 8 * st, kBlockBytes);
+        bulk_g2s(smem0 + st * kDecStage, rec0 + (static_cast<size_t>(j) * p.groups + gi) * kBlockBytes, kBlockBytes, bar_wfull + 8 * st, pol);
+        if (p.trace && blockIdx.x == 0 && r < 100) g_dec_trace[kDecTraceCtas * kDecTraceSlots + 3 * r] = clock64() - t_entry;
       }
+      __syncwarp();
       if (++st == NS) { st = 0; ++it; }
       if (++gi == ng) { gi = 0; ++j; }
     }
@@ -256,96 +258,68 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
     // inside an `elect.sync` region ptxas keeps descriptors and TMEM addresses in uniform registers; under a plain
     // `lane == 0` branch every tcgen05.mma was wrapped in a divergence loop (~15 instructions, ~120 cycles per MMA,
     // tools/mma_probe.cu) and the single issuing thread, not the tensor pipe, bounded the kernel.
-    if (p.c > 1) cluster_arrive_release();   // #1
-    {
-      const uint32_t idesc = instr_desc<T>(kDecN);
-      mbar_wait(bar_xb, 0);   // B operand rows written (generic proxy) and fenced by the workers
-      const int nacc = p.nacc;
-      const uint64_t desc_hi = smem_desc_kmajor(0, kDecN * 16, 128);   // everything but the start address
-      int set = 0, use = 0, j = 0, gi = 0;
+    const uint32_t idesc = instr_desc<T>(kDecN);
+    mbar_wait(bar_xb, 0);   // B operand rows written (generic proxy) and fenced by the workers
+    const uint64_t desc_hi = smem_desc_kmajor(0, kDecN * 16, 128);   // everything but the start address
+    int set = 0, use = 0, j = 0, gi = 0;
 #pragma unroll 1
-      for (int r = 0; r < nrounds; ++r) {
-        if (gi == 0 && j >= 2) mbar_wait(bar_dfree + 8 * (j & 1), ((j >> 1) - 1) & 1);   // D buffer read back by its previous user
-        mbar_wait(bar_afull + 8 * set, use & 1);
-        tc_fence_after();
-        // consecutive k16 steps go to `nacc` independent accumulators, summed (fixed order) when D is read back
-        const uint32_t td = tmem + d_col0 + (j & 1) * (nacc * kDecN), ta = tmem + set * 64;
-        const uint64_t bdesc0 = desc_hi | static_cast<uint64_t>(((xb + gi * (kDecN * 256)) >> 4) & 0x3FFF);
-        if (elect_one()) {
+    for (int r = 0; r < nrounds; ++r) {
+      if (gi == 0 && j >= 2) mbar_wait(bar_dfree + 8 * (j & 1), ((j >> 1) - 1) & 1);   // D buffer read back by its previous user
+      mbar_wait(bar_afull + 8 * set, use & 1);
+      tc_fence_after();
+      const uint32_t td = tmem + d_col0 + (j & 1) * kDecN, ta = tmem + set * 64;
+      const uint64_t bdesc0 = desc_hi | static_cast<uint64_t>(((xb + gi * (kDecN * 256)) >> 4) & 0x3FFF);
+      if (elect_one()) {
 #pragma unroll
-          for (int s = 0; s < 8; ++s)
-            tc_mma_ts(td + (s & (nacc - 1)) * kDecN, ta + 8 * s, bdesc0 + s * ((kDecN * 32) >> 4), idesc, (gi != 0 || s >= nacc) ? 1u : 0u);
-          tc_commit(bar_afree + 8 * set);
-          if (gi == ng - 1) tc_commit(bar_dfull + 8 * (j & 1));
-        }
-        __syncwarp();
-        if (++set == SETS) { set = 0; ++use; }
-        if (++gi == ng) { gi = 0; ++j; }
+        for (int s = 0; s < 8; ++s) tc_mma_ts(td, ta + 8 * s, bdesc0 + s * ((kDecN * 32) >> 4), idesc, (gi | s) ? 1u : 0u);
+        tc_commit(bar_afree + 8 * set);
+        if (gi == ng - 1) tc_commit(bar_dfull + 8 * set);   // the set that dequantised the block's last group reads D back
       }
+      __syncwarp();
+      if (++set == SETS) { set = 0; ++use; }
+      if (++gi == ng) { gi = 0; ++j; }
     }
   } else {
     // ================= workers
     const int wi = warp, e = wi >> 2, q = warp & 3;
     const int L128 = 32 * q + lane;               // output column inside the 128-column block = TMEM lane
-    const int tsel = L128 >> 4, row = L128 & 15;  // which of the block's 8 tiles, row inside it
     const uint32_t lane_base = static_cast<uint32_t>(32 * q) << 16;
-    const uint32_t rot = scratch + wi * p.rot_bytes;
     DEC_TRACE(2);
     pdl_wait();  // x may have been written by the previous kernel
     DEC_TRACE(3);
-    {
-      const int M = p.M;
-      if (M == 1) dec_prologue<T, 1>(p, rm, part, g_begin, ng, wi, kWorkers, lane, rot, xb, t_entry);
-      else if (M == 2) dec_prologue<T, 2>(p, rm, part, g_begin, ng, wi, kWorkers, lane, rot, xb, t_entry);
-      else if (M <= 4) dec_prologue<T, 4>(p, rm, part, g_begin, ng, wi, kWorkers, lane, rot, xb, t_entry);
-      else if (M <= 8) dec_prologue<T, 8>(p, rm, part, g_begin, ng, wi, kWorkers, lane, rot, xb, t_entry);
-      else dec_prologue<T, 16>(p, rm, part, g_begin, ng, wi, kWorkers, lane, rot, xb, t_entry);
+    if (wi < ng && wi < p.rot_warps) {
+      const uint32_t rot = smem0 + p.rot_off + wi * p.rot_bytes;
+      const int M = p.M, rw = p.rot_warps;
+      if (M == 1) dec_prologue<T, 1>(p, rm, part, g_begin, ng, wi, rw, lane, rot, xb, t_entry);
+      else if (M == 2) dec_prologue<T, 2>(p, rm, part, g_begin, ng, wi, rw, lane, rot, xb, t_entry);
+      else if (M <= 4) dec_prologue<T, 4>(p, rm, part, g_begin, ng, wi, rw, lane, rot, xb, t_entry);
+      else if (M <= 8) dec_prologue<T, 8>(p, rm, part, g_begin, ng, wi, rw, lane, rot, xb, t_entry);
+      else dec_prologue<T, 16>(p, rm, part, g_begin, ng, wi, rw, lane, rot, xb, t_entry);
+      fence_proxy_async_smem();  // B rows were written through the generic proxy, tcgen05.mma reads them through the async proxy
     }
-    fence_proxy_async_smem();  // B rows were written through the generic proxy, tcgen05.mma reads them through the async proxy
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_xb);
-    // the rotation tiles are dead from here on: peers may now use the same bytes as my DSMEM receive buffer
-    if (p.c > 1) cluster_arrive_release();  // #1 -- waited on before the first DSMEM push
     DEC_TRACE(4);
 
     const int M = p.M;
-    // scale / zero of (my column, group): small and L2-resident, read straight from the packed records one
-    // of this set's rounds ahead so the latency never sits in front of the dequant
-    const uint32_t qp_row = static_cast<uint32_t>(p.gps) * kUnitWeightBytes + row * 2;
-    const uint32_t zp_row = static_cast<uint32_t>(p.gps) * (kUnitWeightBytes + 32) + row;
-    auto fetch_qparam = [&](int j, int gi, bool ok, uint32_t &sbits, uint32_t &z) {
-      sbits = 0; z = 0;
-      if (ok) {
-        const int g = g_begin + gi, ls = g >> p.gps_shift, u = g & (p.gps - 1);
-        const uint8_t *rec = rec_part + (static_cast<size_t>(ls) * tp + (cb_begin + j) * 8 + tsel) * p.rec_bytes;
-        sbits = __ldg(reinterpret_cast<const uint16_t *>(rec + qp_row + u * 32));
-        z = __ldg(rec + zp_row + u * 16);
-      }
-    };
-
     int j = 0, gi = e;
     while (gi >= ng && j < nj) { gi -= ng; ++j; }
     int st = e, use = 0;
-    uint32_t par = 0;
-    uint32_t sbits, z;
-    fetch_qparam(j, gi, e < nrounds, sbits, z);
+    uint32_t par = 0, epi = 0;
     const uint32_t ta = tmem + lane_base + e * 64;
-    const uint32_t unit_off = tsel * kUnitWeightBytes + row * 16;
+    const uint32_t col_off = (L128 >> 4) * 1024 + (L128 & 15) * 16;   // my 16-byte slots inside a record's weights
     bool first = true;
 #pragma unroll 1
     for (int r = e; r < nrounds; r += SETS) {
-      int gi2 = gi + SETS, j2 = j;
-      while (gi2 >= ng) { gi2 -= ng; ++j2; }
-      uint32_t sbits_next, z_next;
-      fetch_qparam(j2, gi2, r + SETS < nrounds, sbits_next, z_next);
       mbar_wait(bar_wfull + 8 * st, par);
       if (first) { DEC_TRACE(5); first = false; }
-      if (p.trace && q == 0 && lane == 0 && blockIdx.x == 0 && r < 100) g_dec_trace[200 * kDecTraceSlots + 3 * r + 1] = clock64() - t_entry;
+      if (p.trace && q == 0 && lane == 0 && blockIdx.x == 0 && r < 100) g_dec_trace[kDecTraceCtas * kDecTraceSlots + 3 * r + 1] = clock64() - t_entry;
+      const uint32_t rec = smem0 + st * kDecStage;
+      RowDequant<T> dq;
+      dq.prep(lds16(rec + kBlockScaleOff + 2 * L128), lds8(rec + kBlockZeroOff + L128));
       if (use > 0) mbar_wait(bar_afree + 8 * e, (use - 1) & 1);  // the MMAs of my previous round have drained my A buffer
       tc_fence_after();
-      RowDequant<T> dq;
-      dq.prep(sbits, z);
-      const uint32_t wbase = smem0 + st * 8192 + unit_off;
+      const uint32_t wbase = rec + col_off;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const uint4 w4 = lds128(wbase + c * 256);
@@ -362,40 +336,31 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
       if (lane == 0) {
         mbar_arrive(bar_afull + 8 * e);
         mbar_arrive(bar_wempty + 8 * st);
-        if (p.trace && q == 0 && blockIdx.x == 0 && r < 100) g_dec_trace[200 * kDecTraceSlots + 3 * r + 2] = clock64() - t_entry;
+        if (p.trace && q == 0 && blockIdx.x == 0 && r < 100) g_dec_trace[kDecTraceCtas * kDecTraceSlots + 3 * r + 2] = clock64() - t_entry;
       }
       if (gi == ng - 1) {
         // ---- this set closed block j: read D back, one value per token
         const int b = j & 1;
-        mbar_wait(bar_dfull + 8 * b, (j >> 1) & 1);
+        mbar_wait(bar_dfull + 8 * e, epi & 1);
+        ++epi;
         tc_fence_after();
         uint32_t v[16];
-        {
-          const uint32_t td = tmem + lane_base + d_col0 + b * (p.nacc * kDecN);
-          if (M <= 8) tc_ld8(td, v);
-          else tc_ld16(td, v);
-          tc_wait_ld();
-          for (int a = 1; a < p.nacc; ++a) {
-            uint32_t w[16];
-            if (M <= 8) tc_ld8(td + a * kDecN, w);
-            else tc_ld16(td + a * kDecN, w);
-            tc_wait_ld();
-#pragma unroll
-            for (int m = 0; m < 16; ++m)
-              if (m < 8 || M > 8) v[m] = __float_as_uint(__uint_as_float(v[m]) + __uint_as_float(w[m]));
-          }
-        }
+        if (M <= 8) tc_ld8(tmem + lane_base + d_col0 + b * kDecN, v);
+        else tc_ld16(tmem + lane_base + d_col0 + b * kDecN, v);
+        tc_wait_ld();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_dfree + 8 * b);
         if (p.c == 1) {
-          const int n = (p.part_tile_begin[part] + (cb_begin + j) * 8) * kTileN + L128;
+          const int n = n_first + j * kBlockN + L128;
+          if (n < n_end) {
 #pragma unroll
-          for (int m = 0; m < 16; ++m)
-            if (m < M) dec_store<T>(p, __uint_as_float(v[m]), m, n);
+            for (int m = 0; m < 16; ++m)
+              if (m < M) dec_store<T>(p, __uint_as_float(v[m]), m, n);
+          }
         } else {
-          if (!cluster_ready) { cluster_wait_acquire(); cluster_ready = true; }  // #1: every peer is past its prologue
-          const uint32_t dst = map_to_rank(scratch + (((j >> p.c_shift) << p.c_shift) + slice) * (M * 512) + L128 * 4, j & (p.c - 1));
+          if (!cluster_ready) { cluster_wait_acquire(); cluster_ready = true; }  // #1: every peer CTA is running
+          const uint32_t dst = map_to_rank(recv + (((j >> p.c_shift) << p.c_shift) + slice) * (M * 512) + L128 * 4, j & (p.c - 1));
 #pragma unroll
           for (int m = 0; m < 16; ++m)
             if (m < M) st_cluster_f32(dst + m * 512, __uint_as_float(v[m]));
@@ -404,8 +369,8 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
       st += SETS;
       if (st >= NS) { st -= NS; par ^= 1; }
       ++use;
-      gi = gi2; j = j2;
-      sbits = sbits_next; z = z_next;
+      gi += SETS;
+      while (gi >= ng) { gi -= ng; ++j; }
     }
     DEC_TRACE(6);
   }
@@ -426,14 +391,14 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
         const int jo = idx / per, o = idx - jo * per;
         const int m = o >> 7, col = o & 127;
         float acc = 0.f;
-        for (int src = 0; src < p.c; ++src) acc += lds_f32(scratch + ((jo << p.c_shift) + src) * (M * 512) + o * 4);
-        const int j = (jo << p.c_shift) + slice;
-        dec_store<T>(p, acc, m, (p.part_tile_begin[part] + (cb_begin + j) * 8) * kTileN + col);
+        for (int src = 0; src < p.c; ++src) acc += lds_f32(recv + ((jo << p.c_shift) + src) * (M * 512) + o * 4);
+        const int n = n_first + ((jo << p.c_shift) + slice) * kBlockN + col;
+        if (n < n_end) dec_store<T>(p, acc, m, n);
       }
     }
   }
   DEC_TRACE(8);
-  if (p.trace && threadIdx.x == 0 && blockIdx.x < 200) g_dec_trace[blockIdx.x * kDecTraceSlots + 11] = globaltimer_ns();
+  if (p.trace && threadIdx.x == 0 && blockIdx.x < kDecTraceCtas) g_dec_trace[blockIdx.x * kDecTraceSlots + 11] = globaltimer_ns();
   tc_fence_before();
   __syncthreads();
   if (warp == kWorkers + 1) {
@@ -442,8 +407,8 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
   }
 }
 
-int decode2_trace_read(unsigned long long *host, int max_ctas) {
-  const size_t n = static_cast<size_t>(max_ctas < kDecTraceMaxCtas ? max_ctas : kDecTraceMaxCtas) * kDecTraceSlots;
+int decode_trace_read(unsigned long long *host, int max_ctas) {
+  const size_t n = static_cast<size_t>(max_ctas < kDecTraceRows ? max_ctas : kDecTraceRows) * kDecTraceSlots;
   PARO_CUDA_OK(cudaMemcpyFromSymbol(host, g_dec_trace, n * sizeof(unsigned long long)));
   return PARO_OK;
 }
@@ -465,7 +430,7 @@ static bool dec_split_ranges(const Layout &L, int ranges, DecPlan &plan) {
   int cb[PARO_MAX_PARTS], alloc[PARO_MAX_PARTS], total = 0;
   double frac[PARO_MAX_PARTS];
   for (int p = 0; p < L.n_parts; ++p) {
-    cb[p] = (L.part_tile_begin[p + 1] - L.part_tile_begin[p]) / 8;
+    cb[p] = L.part_block_begin[p + 1] - L.part_block_begin[p];
     total += cb[p];
   }
   if (ranges > total) ranges = total;
@@ -506,34 +471,38 @@ static bool dec_split_ranges(const Layout &L, int ranges, DecPlan &plan) {
   return plan.ranges > 0;
 }
 
-bool decode2_supported(const Layout &L, int64_t M) {
-  if (M < 1 || M > 16) return false;
-  if (dec_env_int("PARO_DECODE_V1", 0)) return false;
-  for (int p = 0; p < L.n_parts; ++p)
-    if ((L.part_tile_begin[p + 1] - L.part_tile_begin[p]) % 8) return false;   // partitions of whole 128-column blocks
-  return true;
-}
+struct DecSmem { int xb_off, rot_off, recv_off, bar_off, nstages, rot_warps, total; };
 
-struct DecSmem { int xb_off, scratch_off, bar_off, nstages, total; };
-
-static bool dec_carve(const DecPlan &plan, int M, int rot_bytes, int sets, DecSmem &s) {
+static bool dec_carve_with(const DecPlan &plan, int M, int rot_bytes, int sets, int rot_warps, DecSmem &s) {
   const int xb_bytes = plan.ng_max * kDecN * 256;
-  const int rot_total = 4 * sets * rot_bytes;
+  const int rot_total = (rot_warps * rot_bytes + 127) / 128 * 128;
   const int recv = plan.c > 1 ? ((plan.nj_max + plan.c - 1) / plan.c) * plan.c * M * 512 : 0;
-  const int scr = rot_total > recv ? rot_total : recv;
   const int bar_bytes = 16 * kDecMaxStages + 256;
-  const int fixed = xb_bytes + (scr + 127) / 128 * 128 + bar_bytes;
-  int nst = (kDecSmemLimit - fixed) / 8192;
+  const int fixed = xb_bytes + rot_total + recv + bar_bytes + 128;
+  int nst = (kDecSmemLimit - fixed) / kDecStage;
   if (nst > kDecMaxStages) nst = kDecMaxStages;
   const int want = dec_env_int("PARO_DECODE_STAGES", 0);
   if (want >= sets && want < nst) nst = want;
-  if (nst < sets + 2) return false;
+  nst = nst / sets * sets;   // a stage is always consumed by the same set
+  if (nst < sets) return false;
   s.nstages = nst;
-  s.xb_off = nst * 8192;
-  s.scratch_off = s.xb_off + xb_bytes;
-  s.bar_off = s.scratch_off + (scr + 127) / 128 * 128;
+  s.rot_warps = rot_warps;
+  s.xb_off = (nst * kDecStage + 127) / 128 * 128;
+  s.rot_off = s.xb_off + xb_bytes;
+  s.recv_off = s.rot_off + rot_total;
+  s.bar_off = s.recv_off + (recv + 127) / 128 * 128;
   s.total = s.bar_off + bar_bytes;
-  return true;
+  return s.total <= kDecSmemLimit;
+}
+
+// every group gets its own rotating warp when the tiles fit; otherwise fewer warps take several groups each
+static bool dec_carve(const DecPlan &plan, int M, int rot_bytes, int sets, DecSmem &s) {
+  int rw = plan.ng_max < 4 * sets ? plan.ng_max : 4 * sets;
+  for (;;) {
+    if (dec_carve_with(plan, M, rot_bytes, sets, rw, s)) return true;
+    if (rw <= 2) return false;
+    rw = rw > 8 ? 8 : rw / 2;
+  }
 }
 
 // how many clusters of `c` CTAs with this footprint the device keeps resident (GPC granularity); cached per thread
@@ -565,7 +534,7 @@ static int max_resident_clusters(int c, int smem_bytes, int sms) {
 }
 
 template <typename T, int SETS>
-static int launch_decode2(DecParams &p, const Layout &L, int sms, cudaStream_t stream) {
+static int launch_decode(DecParams &p, const Layout &L, int sms, cudaStream_t stream) {
   auto kern = decode_kernel<T, SETS>;
   const bool cluster_ok = !dec_env_int("PARO_NO_CLUSTER", 0);
   const int force_c = dec_env_int("PARO_DECODE_C", 0);
@@ -625,15 +594,18 @@ static int launch_decode2(DecParams &p, const Layout &L, int sms, cudaStream_t s
   cfg.numAttrs = na;
   p.c = best.c; p.c_shift = best.c_shift;
   p.nstages = best_s.nstages;
-  p.xb_off = best_s.xb_off; p.scratch_off = best_s.scratch_off; p.bar_off = best_s.bar_off;
+  p.rot_warps = best_s.rot_warps;
+  p.xb_off = best_s.xb_off; p.rot_off = best_s.rot_off; p.recv_off = best_s.recv_off; p.bar_off = best_s.bar_off;
   for (int i = 0; i <= PARO_MAX_PARTS; ++i) p.part_range_begin[i] = best.part_range_begin[i];
   PARO_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
   note_launches(1);
   return PARO_OK;
 }
 
-int decode2_forward(const paro_linear_shape &s, const Layout &L, const void *packed, const void *x, int64_t M,
-                    const void *bias, void *y, cudaStream_t stream) {
+bool decode_supported(const Layout &L, int64_t M) { return M >= 1 && M <= 16 && L.groups >= 1; }
+
+int decode_forward(const paro_linear_shape &s, const Layout &L, const void *packed, const void *x, int64_t M,
+                   const void *bias, void *y, cudaStream_t stream) {
   int dev = 0, sms = 0;
   PARO_CUDA_OK(cudaGetDevice(&dev));
   PARO_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -642,26 +614,22 @@ int decode2_forward(const paro_linear_shape &s, const Layout &L, const void *pac
   p.x = x; p.y = y; p.bias = bias;
   p.M = static_cast<int>(M); p.K = L.K; p.N = L.N;
   p.n_parts = L.n_parts; p.groups = L.groups; p.krot = L.krot;
-  p.gps = L.gps; p.gps_shift = L.gps == 16 ? 4 : 3; p.lslices = L.slices; p.rec_bytes = L.rec_bytes;
   p.rot_bytes = kGroup * 2 * (M == 1 ? 1 : M == 2 ? 2 : M <= 4 ? 4 : M <= 8 ? 8 : 16);
   p.trace = dec_env_int("PARO_DECODE_TRACE", 0);
-  p.fake1 = dec_env_int("PARO_DECODE_FAKE1", 0);
-  for (int i = 0; i <= PARO_MAX_PARTS; ++i) p.part_tile_begin[i] = L.part_tile_begin[i];
+  for (int i = 0; i <= PARO_MAX_PARTS; ++i) {
+    p.part_col_begin[i] = L.part_col_begin[i];
+    p.part_block_begin[i] = L.part_block_begin[i];
+  }
   p.meta_group_bytes = L.meta_group_bytes;
   p.meta_off = static_cast<long long>(L.meta_off);
   p.rec_off = static_cast<long long>(L.rec_off);
-  const int sets = dec_env_int("PARO_DECODE_SETS", 6);
-  // TMEM: sets x 64 columns of A + 2 D buffers x nacc accumulators x 16 columns
-  int nacc = dec_env_int("PARO_DECODE_NACC", 4);
-  nacc = nacc >= 8 ? 8 : nacc >= 4 ? 4 : nacc >= 2 ? 2 : 1;
-  while (64 * (sets == 5 || sets == 7 || sets == 4 ? sets : 6) + 2 * nacc * kDecN > kDecTmemCols) nacc >>= 1;
-  p.nacc = nacc;
+  const int sets = dec_env_int("PARO_DECODE_SETS", 5);   // 5 sets x 4 dequant warps measured best (tools/microbench.py); 4..7 selectable
   const bool bf16 = s.dtype == PARO_BF16;
   switch (sets) {
-    case 4: return bf16 ? launch_decode2<__nv_bfloat16, 4>(p, L, sms, stream) : launch_decode2<__half, 4>(p, L, sms, stream);
-    case 5: return bf16 ? launch_decode2<__nv_bfloat16, 5>(p, L, sms, stream) : launch_decode2<__half, 5>(p, L, sms, stream);
-    case 7: return bf16 ? launch_decode2<__nv_bfloat16, 7>(p, L, sms, stream) : launch_decode2<__half, 7>(p, L, sms, stream);
-    default: return bf16 ? launch_decode2<__nv_bfloat16, 6>(p, L, sms, stream) : launch_decode2<__half, 6>(p, L, sms, stream);
+    case 4: return bf16 ? launch_decode<__nv_bfloat16, 4>(p, L, sms, stream) : launch_decode<__half, 4>(p, L, sms, stream);
+    case 7: return bf16 ? launch_decode<__nv_bfloat16, 7>(p, L, sms, stream) : launch_decode<__half, 7>(p, L, sms, stream);
+    case 6: return bf16 ? launch_decode<__nv_bfloat16, 6>(p, L, sms, stream) : launch_decode<__half, 6>(p, L, sms, stream);
+    default: return bf16 ? launch_decode<__nv_bfloat16, 5>(p, L, sms, stream) : launch_decode<__half, 5>(p, L, sms, stream);
   }
 }
 

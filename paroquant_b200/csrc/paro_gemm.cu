@@ -11,9 +11,9 @@
 //   D  = fp32 [128 x NT] in TMEM (NT <= 256 columns), one rounding to T in the epilogue, bias in T.
 //
 // CTA = one (128-column block of N) x (NT-token block of M) output tile over the whole K.
-// Warp roles as in paro_tc.cu: warp 0 TMA producer (8 x 1 KB weight units + 2 B stages per
+// Warp roles as in paro_tc.cu: warp 0 TMA producer (one 8576-byte weight record + 2 B stages per
 // round), warp 1 TMEM allocator + single-thread tcgen05.mma issuer, warps 2-17 four dequant sets
-// (thread = one output column; round r -> set r % 4, A buffer r % 3), all of them read D back.
+// (thread = one output column; round r -> set r % 4, each set owns one A buffer), all of them read D back.
 // At NT = 256 one round is 8 MMAs x 128 cycles on the tensor pipe against ~260 dequant
 // instructions per worker thread: the CUDA cores idle, the tensor core does not.
 #include "paro_common.cuh"
@@ -21,9 +21,6 @@
 
 namespace paro {
 
-size_t decode_workspace_bytes(const Layout &L, int64_t max_m);
-int decode_forward(const paro_linear_shape &s, const Layout &L, const void *packed, const void *x, int64_t M,
-                   const void *bias, void *y, void *workspace, size_t workspace_bytes, cudaStream_t stream);
 int rotate_tiled_launch(const void *x, void *out, const int16_t *idx, const void *theta, int theta_dtype, const void *scales,
                         int scales_dtype, int64_t M, int64_t M_store, int tiled_nt, int K, int krot, int dtype, cudaStream_t stream);
 
@@ -32,7 +29,8 @@ constexpr int kGemmThreads = 32 * (3 + 4 * kGemmSets);   // + weight producer, M
 constexpr int kGemmTmemCols = 512;
 constexpr int kWStages = 8;   // rounds of weights in flight (8 KB each); a multiple of kGemmSets
 constexpr int kBStages = 4;   // k64 stages of x_rot in flight (NT * 128 bytes each)
-constexpr int kABufs = 3;
+constexpr int kABufs = kGemmSets;   // one A buffer (64 TMEM columns) per dequant set; D takes the other 256 columns
+constexpr int kWStage = kBlockBytes;   // one (block, group) record per ring stage
 
 struct GemmParams {
   const uint8_t *packed;
@@ -40,8 +38,9 @@ struct GemmParams {
   void *y;
   const void *bias;
   int M, K, N, NT, n_blocks, tok_blocks;
-  int n_parts, slices, groups, gps, rec_bytes, tiles_total;
-  int part_tile_begin[PARO_MAX_PARTS + 1];
+  int n_parts, groups;
+  int part_col_begin[PARO_MAX_PARTS + 1];
+  int part_block_begin[PARO_MAX_PARTS + 1];
   long long rec_off, xr_part_stride;
 };
 
@@ -83,6 +82,11 @@ __device__ __forceinline__ uint64_t g_desc_kmajor(uint32_t addr, uint32_t lbo, u
 template <typename T> __device__ __forceinline__ uint32_t g_instr_desc(int n) {
   const uint32_t fmt = Traits<T>::code == PARO_BF16 ? 1u : 0u;
   return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (8u << 24);
+}
+__device__ __forceinline__ uint32_t g_lds8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ bool g_elect_one() {
   uint32_t pred;
@@ -128,18 +132,6 @@ template <> struct GRowDequant<__half> {
   }
 };
 
-__device__ __forceinline__ int part_of_tile(const GemmParams &p, int tile_g) {
-  int part = 0;
-  while (part + 1 < p.n_parts && tile_g >= p.part_tile_begin[part + 1]) ++part;
-  return part;
-}
-// byte offset of the record (slice, tile_g) inside packed
-__device__ __forceinline__ size_t record_offset(const GemmParams &p, int slice, int tile_g, int part) {
-  const int tp = p.part_tile_begin[part + 1] - p.part_tile_begin[part];
-  return static_cast<size_t>(p.rec_off) + (static_cast<size_t>(p.slices) * p.part_tile_begin[part] + static_cast<size_t>(slice) * tp +
-                                           (tile_g - p.part_tile_begin[part])) * p.rec_bytes;
-}
-
 template <typename T>
 __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const GemmParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -147,14 +139,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const GemmPara
   const int NT = p.NT;
   const uint32_t smem0 = smem_u32(smem);
   const uint32_t b_stage_bytes = NT * 128;
-  const uint32_t w_ring = smem0, b_ring = smem0 + kWStages * 8192;
+  const uint32_t w_ring = smem0, b_ring = smem0 + kWStages * kWStage;
   const uint32_t bars = b_ring + kBStages * b_stage_bytes;
   const uint32_t bar_wfull = bars, bar_wempty = bars + 64, bar_bfull = bars + 128, bar_bempty = bars + 160;
   const uint32_t bar_afull = bars + 192, bar_afree = bars + 224, bar_dfull = bars + 256, tmem_slot = bars + 264;
 
-  const int block = blockIdx.x % p.n_blocks, tb = blockIdx.x / p.n_blocks;
-  const int tile0 = block * 8;                                  // first 16-column tile of this 128-column block
-  const int part = part_of_tile(p, tile0);                      // blocks never straddle partitions (host check)
+  const int block = blockIdx.x % p.n_blocks, tb = blockIdx.x / p.n_blocks;   // 128-column block (over all partitions), token block
+  int part = 0;
+  while (block >= p.part_block_begin[part + 1]) ++part;
+  const int n0 = p.part_col_begin[part] + (block - p.part_block_begin[part]) * kBlockN, n_end = p.part_col_begin[part + 1];
   const int rounds = p.groups;
 
   if (threadIdx.x == 0) {
@@ -178,19 +171,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const GemmPara
     // ================= weight producer: independent of the pre-pass; every 128-column block is re-read by
     // all token blocks, so the units stay under the normal L2 policy (no evict-first here)
     if (lane == 0) {
-      int valid_tiles = p.tiles_total - tile0;
-      if (valid_tiles > 8) valid_tiles = 8;
+      const uint8_t *rec = p.packed + p.rec_off + static_cast<size_t>(block) * p.groups * kBlockBytes;
       for (int r = 0; r < rounds; ++r) {
         const int ws = r % kWStages, wit = r / kWStages;
         if (wit > 0) mbar_wait(bar_wempty + 8 * ws, (wit - 1) & 1);
-        const int slice = r / p.gps, u = r - slice * p.gps;
-        mbar_arrive_expect_tx(bar_wfull + 8 * ws, valid_tiles * kUnitWeightBytes);
-        for (int t = 0; t < valid_tiles; ++t)
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(w_ring + ws * 8192 + t * kUnitWeightBytes),
-                         "l"(p.packed + record_offset(p, slice, tile0 + t, part) + u * kUnitWeightBytes), "r"(kUnitWeightBytes),
-                         "r"(bar_wfull + 8 * ws)
-                       : "memory");
+        mbar_arrive_expect_tx(bar_wfull + 8 * ws, kBlockBytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(w_ring + ws * kWStage), "l"(rec + static_cast<size_t>(r) * kBlockBytes), "r"(kBlockBytes), "r"(bar_wfull + 8 * ws)
+                     : "memory");
       }
     }
   } else if (warp == kGemmThreads / 32 - 1) {
@@ -217,7 +205,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const GemmPara
       const uint32_t idesc = g_instr_desc<T>(NT);
       const uint32_t step_bytes = NT * 32, lbo = NT * 16;
       const uint64_t desc_hi = g_desc_kmajor(0, lbo, 128);
-      int abuf = 0, a_use = 0;
+      int abuf = 0, a_use = 0;   // A buffer of round r = its dequant set = r % kGemmSets, r / kGemmSets earlier uses
       for (int r = 0; r < rounds; ++r) {
         mbar_wait(bar_afull + 8 * abuf, a_use & 1);
         for (int hstage = 0; hstage < 2; ++hstage) {
@@ -245,35 +233,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const GemmPara
   } else {
     // ================= workers: thread = one output column (TMEM lane)
     const int wi = warp - 2, e = wi >> 2, q = warp & 3;
-    const int L128 = 32 * q + lane;                // row inside the 128-column block
-    const int tsel = L128 >> 4, row = L128 & 15;   // which of the block's 8 tiles, row inside it
-    const int tile_g = tile0 + tsel;
-    const bool tile_ok = tile_g < p.tiles_total;
+    const int L128 = 32 * q + lane;                // column inside the 128-column block = TMEM lane
     const uint32_t lane_base = static_cast<uint32_t>(32 * q) << 16;
-    // scale and zero of (this column, group r): small and L2-resident, read straight from the packed records,
-    // always one of this set's rounds ahead so the latency never sits in front of the dequant
-    auto fetch_qparam = [&](int r, uint32_t &sbits, uint32_t &z) {
-      sbits = 0; z = 0;
-      if (tile_ok && r < rounds) {
-        const int slice = r / p.gps, u = r - slice * p.gps;
-        const uint8_t *rec = p.packed + record_offset(p, slice, tile_g, part);
-        sbits = *reinterpret_cast<const uint16_t *>(rec + p.gps * kUnitWeightBytes + u * 32 + row * 2);
-        z = rec[p.gps * (kUnitWeightBytes + 32) + u * 16 + row];
-      }
-    };
-    uint32_t sbits, z, sbits_next, z_next;
-    fetch_qparam(e, sbits, z);
-    int abuf = e % kABufs, a_use = e / kABufs;
+    const uint32_t col_off = (L128 >> 4) * 1024 + (L128 & 15) * 16;   // my 16-byte slots inside a record's weights
+    // Every barrier has ONE waiting party per phase sequence (set e waits only on its own A buffer's barriers): with
+    // A buffers shared between sets, a fast set could ask for a phase two ahead of the barrier and the parity test
+    // passes on the stale phase (seen as a hang / wrong results once the weight stream stopped pacing the workers).
+    const uint32_t ta = tmem + lane_base + e * 64;
+    int use = 0;
     for (int r = e; r < rounds; r += kGemmSets) {
       const int ws = r % kWStages;
-      fetch_qparam(r + kGemmSets, sbits_next, z_next);
       mbar_wait(bar_wfull + 8 * ws, (r / kWStages) & 1);
-      if (a_use > 0) mbar_wait(bar_afree + 8 * abuf, (a_use - 1) & 1);
-      g_fence_after();
+      const uint32_t rec = w_ring + ws * kWStage;
       GRowDequant<T> dq;
-      dq.prep(sbits, z);
-      const uint32_t wbase = w_ring + ws * 8192 + tsel * kUnitWeightBytes + row * 16;
-      const uint32_t ta = tmem + lane_base + abuf * 64;
+      dq.prep(lds16(rec + kBlockScaleOff + 2 * L128), g_lds8(rec + kBlockZeroOff + L128));   // zero-filled past the partition's end
+      if (use > 0) mbar_wait(bar_afree + 8 * e, (use - 1) & 1);
+      g_fence_after();
+      const uint32_t wbase = rec + col_off;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const uint4 w4 = lds128(wbase + c * 256);
@@ -282,31 +258,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const GemmPara
         dq.word(w4.y, regs + 4);
         dq.word(w4.z, regs + 8);
         dq.word(w4.w, regs + 12);
-        if (!tile_ok) {
-#pragma unroll
-          for (int k = 0; k < 16; ++k) regs[k] = 0u;
-        }
         g_st16(ta + 16 * c, regs);
       }
       g_wait_st();
       g_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(bar_afull + 8 * abuf);
+        mbar_arrive(bar_afull + 8 * e);
         mbar_arrive(bar_wempty + 8 * ws);
       }
-      sbits = sbits_next;
-      z = z_next;
-      abuf += kGemmSets % kABufs;                 // (r + 4) % 3 and (r + 4) / 3, carried incrementally
-      a_use += kGemmSets / kABufs;
-      if (abuf >= kABufs) { abuf -= kABufs; ++a_use; }
+      ++use;
     }
 
     // ---- epilogue: set e converts its share of the token columns of its lanes
     mbar_wait(bar_dfull, 0);
     g_fence_after();
-    const int n = block * 128 + L128;
-    const bool n_ok = n < p.N;
+    const int n = n0 + L128;
+    const bool n_ok = n < n_end;
     float bias_f = 0.f;
     const bool has_bias = p.bias != nullptr;
     if (has_bias && n_ok) bias_f = Traits<T>::to_float(static_cast<const T *>(p.bias)[n]);
@@ -340,25 +308,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const GemmPara
 // ------------------------------------------------------------------ host side
 static int pick_nt(int64_t M) { return M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256; }
 
-static bool gemm_supported(const Layout &L) {
-  for (int p = 0; p < L.n_parts; ++p)
-    if ((L.part_tile_begin[p + 1] - L.part_tile_begin[p]) % 8) return p == L.n_parts - 1 && L.n_parts == 1;  // blocks must not straddle partitions
-  return true;
-}
-
 size_t gemm_workspace_bytes(const Layout &L, int64_t max_m) {
-  const size_t small = decode_workspace_bytes(L, 16);
-  if (!gemm_supported(L)) return small;
   const int NT = pick_nt(max_m);
   const int64_t m_pad = (max_m + NT - 1) / NT * NT;
-  const size_t xr = static_cast<size_t>(L.n_parts) * m_pad * L.K * 2;
-  return (small + 255) / 256 * 256 + xr;   // x_rot lives behind the small-M region, whose counters must stay zero
+  return static_cast<size_t>(L.n_parts) * m_pad * L.K * 2;   // x_rot per partition, B-operand tile order
 }
 
 template <typename T>
 static int launch_gemm(const GemmParams &p, cudaStream_t stream) {
   auto kern = tc_gemm_kernel<T>;
-  const size_t smem = kWStages * 8192 + static_cast<size_t>(kBStages) * p.NT * 128 + 512;
+  const size_t smem = static_cast<size_t>(kWStages) * kWStage + static_cast<size_t>(kBStages) * p.NT * 128 + 512;
   PARO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(p.n_blocks * p.tok_blocks);
@@ -377,16 +336,6 @@ static int launch_gemm(const GemmParams &p, cudaStream_t stream) {
 
 int gemm_forward(const paro_linear_shape &s, const Layout &L, const void *packed, const void *x, int64_t M,
                  const void *bias, void *y, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
-  if (!gemm_supported(L)) {
-    // partition sizes that are not multiples of 128: rows go through the small-M kernel 16 at a time
-    for (int64_t m0 = 0; m0 < M; m0 += 16) {
-      const int64_t mc = M - m0 < 16 ? M - m0 : 16;
-      const int rc = decode_forward(s, L, packed, static_cast<const uint8_t *>(x) + m0 * L.K * 2, mc, bias,
-                                    static_cast<uint8_t *>(y) + m0 * L.N * 2, workspace, workspace_bytes, stream);
-      if (rc) return rc;
-    }
-    return PARO_OK;
-  }
   if (workspace_bytes < gemm_workspace_bytes(L, M)) {
     set_error("workspace too small: have %zu, need %zu", workspace_bytes, gemm_workspace_bytes(L, M));
     return PARO_EWORKSPACE;
@@ -394,7 +343,7 @@ int gemm_forward(const paro_linear_shape &s, const Layout &L, const void *packed
   const int NT = pick_nt(M);
   const int64_t m_pad = (M + NT - 1) / NT * NT;
   const uint8_t *pk = static_cast<const uint8_t *>(packed);
-  uint8_t *xr_base = static_cast<uint8_t *>(workspace) + (decode_workspace_bytes(L, 16) + 255) / 256 * 256;
+  uint8_t *xr_base = static_cast<uint8_t *>(workspace);
   // ---- pre-pass: one rotation per partition, output in B-operand tile order
   for (int part = 0; part < L.n_parts; ++part) {
     const uint8_t *raw = pk + L.raw_off + part * L.raw_part_bytes;
@@ -409,10 +358,13 @@ int gemm_forward(const paro_linear_shape &s, const Layout &L, const void *packed
   p.y = y;
   p.bias = bias;
   p.M = static_cast<int>(M); p.K = L.K; p.N = L.N; p.NT = NT;
-  p.n_blocks = (L.tiles_total + 7) / 8;
+  p.n_blocks = L.blocks_total;
   p.tok_blocks = static_cast<int>(m_pad / NT);
-  p.n_parts = L.n_parts; p.slices = L.slices; p.groups = L.groups; p.gps = L.gps; p.rec_bytes = L.rec_bytes; p.tiles_total = L.tiles_total;
-  for (int i = 0; i <= PARO_MAX_PARTS; ++i) p.part_tile_begin[i] = L.part_tile_begin[i];
+  p.n_parts = L.n_parts; p.groups = L.groups;
+  for (int i = 0; i <= PARO_MAX_PARTS; ++i) {
+    p.part_col_begin[i] = L.part_col_begin[i];
+    p.part_block_begin[i] = L.part_block_begin[i];
+  }
   p.rec_off = static_cast<long long>(L.rec_off);
   p.xr_part_stride = static_cast<long long>(m_pad) * L.K * 2;
   if (s.dtype == PARO_BF16) return launch_gemm<__nv_bfloat16>(p, stream);

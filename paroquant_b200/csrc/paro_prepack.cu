@@ -24,10 +24,6 @@ __device__ __forceinline__ uint16_t cast_to_T_bits(const void *p, int64_t i, int
   return __bfloat16_as_ushort(__float2bfloat16_rn(f));
 }
 
-struct PartOffsets {
-  int n_begin[PARO_MAX_PARTS + 1];  // first output column of each partition
-};
-
 __global__ void prepack_meta_kernel(Layout L, const int16_t *__restrict__ pairs, const void *__restrict__ theta,
                                     int theta_dtype, const void *__restrict__ cscales, int cs_dtype,
                                     uint8_t *__restrict__ packed) {
@@ -68,98 +64,81 @@ __global__ void prepack_meta_kernel(Layout L, const int16_t *__restrict__ pairs,
 // so that (w >> 4i) & 0x000F000F is the bf16x2 / half2 payload of TMEM column i of the word
 __device__ __constant__ int kNibblePos[8] = {0, 16, 4, 20, 8, 24, 12, 28};
 
-__global__ void prepack_weight_kernel(Layout L, PartOffsets po, const int32_t *__restrict__ qweight,
-                                      uint8_t *__restrict__ packed) {
-  // one thread per output word: (record, unit u, chunk c, row, j)
-  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  const int64_t total = static_cast<int64_t>(L.slices) * L.tiles_total * L.gps * 256;
-  if (idx >= total) return;
-  const int j = idx & 3, row = (idx >> 2) & 15, c = (idx >> 6) & 3;
-  const int u = static_cast<int>((idx >> 8) % L.gps);
-  const int64_t rec = idx / (256 * static_cast<int64_t>(L.gps));
-  // record -> (part, slice, tile)
+// block index over all partitions -> partition
+__device__ __forceinline__ int block_part(const Layout &L, int block) {
   int part = 0;
-  while (rec >= static_cast<int64_t>(L.slices) * L.part_tile_begin[part + 1]) ++part;
-  const int tp = L.part_tile_begin[part + 1] - L.part_tile_begin[part];
-  const int64_t rloc = rec - static_cast<int64_t>(L.slices) * L.part_tile_begin[part];
-  const int slice = rloc / tp, tile = rloc % tp;
-  const int n = po.n_begin[part] + tile * kTileN + row;
-  const int gk = slice * L.gps + u;
+  while (block >= L.part_block_begin[part + 1]) ++part;
+  return part;
+}
+
+__global__ void prepack_weight_kernel(Layout L, const int32_t *__restrict__ qweight, uint8_t *__restrict__ packed) {
+  // one thread per output word: (record = (block, g), t, chunk c, row, j)
+  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t total = static_cast<int64_t>(L.blocks_total) * L.groups * 2048;
+  if (idx >= total) return;
+  const int j = idx & 3, row = (idx >> 2) & 15, c = (idx >> 6) & 3, t = (idx >> 8) & 7;
+  const int64_t rec = idx >> 11;
+  const int block = static_cast<int>(rec / L.groups), g = static_cast<int>(rec % L.groups);
+  const int part = block_part(L, block);
+  const int n = L.part_col_begin[part] + (block - L.part_block_begin[part]) * kBlockN + t * 16 + row;
   uint32_t w = 0;
-  if (gk < L.groups) {
-    const int64_t kb = static_cast<int64_t>(gk) * kGroup + 32 * c + 8 * j;
+  if (n < L.part_col_begin[part + 1]) {
+    const int64_t kb = static_cast<int64_t>(g) * kGroup + 32 * c + 8 * j;
     const int nc8 = L.N / 8;
 #pragma unroll
     for (int e = 0; e < 8; ++e) w |= awq_nibble(qweight, kb + e, n, nc8) << kNibblePos[e];
   }
-  uint32_t *dst = reinterpret_cast<uint32_t *>(packed + L.rec_off + rec * L.rec_bytes);
-  dst[u * 256 + c * 64 + row * 4 + j] = w;
+  reinterpret_cast<uint32_t *>(packed + L.rec_off + rec * kBlockBytes)[idx & 2047] = w;
 }
 
-__global__ void prepack_qparam_kernel(Layout L, PartOffsets po, const int32_t *__restrict__ qzeros,
-                                      const void *__restrict__ scales, int scales_dtype,
-                                      uint8_t *__restrict__ packed) {
-  // one thread per (record, unit u, row)
+__global__ void prepack_qparam_kernel(Layout L, const int32_t *__restrict__ qzeros, const void *__restrict__ scales,
+                                      int scales_dtype, uint8_t *__restrict__ packed) {
+  // one thread per (record, column of the block)
   const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  const int64_t total = static_cast<int64_t>(L.slices) * L.tiles_total * L.gps * 16;
+  const int64_t total = static_cast<int64_t>(L.blocks_total) * L.groups * kBlockN;
   if (idx >= total) return;
-  const int row = idx & 15;
-  const int u = static_cast<int>((idx >> 4) % L.gps);
-  const int64_t rec = idx / (16 * static_cast<int64_t>(L.gps));
-  int part = 0;
-  while (rec >= static_cast<int64_t>(L.slices) * L.part_tile_begin[part + 1]) ++part;
-  const int tp = L.part_tile_begin[part + 1] - L.part_tile_begin[part];
-  const int64_t rloc = rec - static_cast<int64_t>(L.slices) * L.part_tile_begin[part];
-  const int slice = rloc / tp, tile = rloc % tp;
-  const int n = po.n_begin[part] + tile * kTileN + row;
-  const int gk = slice * L.gps + u;
+  const int col = idx & 127;
+  const int64_t rec = idx >> 7;
+  const int block = static_cast<int>(rec / L.groups), g = static_cast<int>(rec % L.groups);
+  const int part = block_part(L, block);
+  const int n = L.part_col_begin[part] + (block - L.part_block_begin[part]) * kBlockN + col;
   uint16_t s = 0;
   uint8_t z = 0;
-  if (gk < L.groups) {
-    s = cast_to_T_bits(scales, static_cast<int64_t>(gk) * L.N + n, scales_dtype, L.dtype);
-    z = static_cast<uint8_t>(awq_nibble(qzeros, gk, n, L.N / 8));
+  if (n < L.part_col_begin[part + 1]) {
+    s = cast_to_T_bits(scales, static_cast<int64_t>(g) * L.N + n, scales_dtype, L.dtype);
+    z = static_cast<uint8_t>(awq_nibble(qzeros, g, n, L.N / 8));
   }
-  uint8_t *rb = packed + L.rec_off + rec * L.rec_bytes;
-  reinterpret_cast<uint16_t *>(rb + L.gps * kUnitWeightBytes)[u * 16 + row] = s;
-  rb[L.gps * (kUnitWeightBytes + 32) + u * 16 + row] = z;
+  uint8_t *rb = packed + L.rec_off + rec * kBlockBytes;
+  reinterpret_cast<uint16_t *>(rb + kBlockScaleOff)[col] = s;
+  rb[kBlockZeroOff + col] = z;
 }
 
 // Inverse, for tests: dense W[k][n] = T((q - z) * s_T), the exact operand the GEMM consumes.
 template <typename T>
-__global__ void unpack_dense_kernel(Layout L, PartOffsets po, const uint8_t *__restrict__ packed, T *__restrict__ W) {
+__global__ void unpack_dense_kernel(Layout L, const uint8_t *__restrict__ packed, T *__restrict__ W) {
   const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (idx >= static_cast<int64_t>(L.K) * L.N) return;
   const int n = idx % L.N;
   const int k = idx / L.N;
   int part = 0;
-  while (n >= po.n_begin[part + 1]) ++part;
-  const int nl = n - po.n_begin[part];
-  const int tile = nl / kTileN, row = nl & 15;
-  const int gk = k / kGroup, slice = gk / L.gps, u = gk % L.gps, kl = k % kGroup;
+  while (n >= L.part_col_begin[part + 1]) ++part;
+  const int nl = n - L.part_col_begin[part];
+  const int block = L.part_block_begin[part] + nl / kBlockN, col = nl % kBlockN;
+  const int t = col >> 4, row = col & 15;
+  const int g = k / kGroup, kl = k % kGroup;
   const int c = kl >> 5, j = (kl >> 3) & 3, e = kl & 7;
-  const uint8_t *rb = packed + L.record_offset(part, slice, tile);
-  const uint32_t w = reinterpret_cast<const uint32_t *>(rb)[u * 256 + c * 64 + row * 4 + j];
+  const uint8_t *rb = packed + L.record_offset(block, g);
+  const uint32_t w = reinterpret_cast<const uint32_t *>(rb)[t * 256 + c * 64 + row * 4 + j];
   const int q = (w >> kNibblePos[e]) & 0xF;
-  const int z = rb[L.gps * (kUnitWeightBytes + 32) + u * 16 + row];
-  const T s = reinterpret_cast<const T *>(rb + L.gps * kUnitWeightBytes)[u * 16 + row];
+  const int z = rb[kBlockZeroOff + col];
+  const T s = reinterpret_cast<const T *>(rb + kBlockScaleOff)[col];
   // (q - z) is exact in T; one rounding in the product, like the fused kernels
   W[idx] = Traits<T>::from_float(static_cast<float>(q - z) * Traits<T>::to_float(s));
-}
-
-static PartOffsets part_offsets(const paro_linear_shape &s) {
-  PartOffsets po;
-  int n = 0;
-  for (int p = 0; p <= PARO_MAX_PARTS; ++p) {
-    po.n_begin[p] = n;
-    if (p < s.n_parts) n += s.part_sizes[p];
-  }
-  return po;
 }
 
 int prepack_launch(const paro_linear_shape &s, const Layout &L, const int32_t *qweight, const int32_t *qzeros,
                    const void *scales, int scales_dtype, const int16_t *pairs, const void *theta, int theta_dtype,
                    const void *cscales, int cs_dtype, void *packed, cudaStream_t stream) {
-  const PartOffsets po = part_offsets(s);
   uint8_t *out = static_cast<uint8_t *>(packed);
   const int B = 256;
   {
@@ -168,13 +147,12 @@ int prepack_launch(const paro_linear_shape &s, const Layout &L, const int32_t *q
                                                                                      cscales, cs_dtype, out);
   }
   {
-    const int64_t total = static_cast<int64_t>(L.slices) * L.tiles_total * L.gps * 256;
-    prepack_weight_kernel<<<static_cast<unsigned>((total + B - 1) / B), B, 0, stream>>>(L, po, qweight, out);
+    const int64_t total = static_cast<int64_t>(L.blocks_total) * L.groups * 2048;
+    prepack_weight_kernel<<<static_cast<unsigned>((total + B - 1) / B), B, 0, stream>>>(L, qweight, out);
   }
   {
-    const int64_t total = static_cast<int64_t>(L.slices) * L.tiles_total * L.gps * 16;
-    prepack_qparam_kernel<<<static_cast<unsigned>((total + B - 1) / B), B, 0, stream>>>(L, po, qzeros, scales,
-                                                                                        scales_dtype, out);
+    const int64_t total = static_cast<int64_t>(L.blocks_total) * L.groups * kBlockN;
+    prepack_qparam_kernel<<<static_cast<unsigned>((total + B - 1) / B), B, 0, stream>>>(L, qzeros, scales, scales_dtype, out);
   }
   PARO_CUDA_OK(cudaGetLastError());
   note_launches(3);
@@ -182,14 +160,13 @@ int prepack_launch(const paro_linear_shape &s, const Layout &L, const int32_t *q
 }
 
 int unpack_dense_launch(const paro_linear_shape &s, const Layout &L, const void *packed, void *W, cudaStream_t stream) {
-  const PartOffsets po = part_offsets(s);
   const int64_t total = static_cast<int64_t>(L.K) * L.N;
   const int B = 256;
   const unsigned grid = static_cast<unsigned>((total + B - 1) / B);
   if (L.dtype == PARO_F16)
-    unpack_dense_kernel<__half><<<grid, B, 0, stream>>>(L, po, static_cast<const uint8_t *>(packed), static_cast<__half *>(W));
+    unpack_dense_kernel<__half><<<grid, B, 0, stream>>>(L, static_cast<const uint8_t *>(packed), static_cast<__half *>(W));
   else
-    unpack_dense_kernel<__nv_bfloat16><<<grid, B, 0, stream>>>(L, po, static_cast<const uint8_t *>(packed),
+    unpack_dense_kernel<__nv_bfloat16><<<grid, B, 0, stream>>>(L, static_cast<const uint8_t *>(packed),
                                                                static_cast<__nv_bfloat16 *>(W));
   PARO_CUDA_OK(cudaGetLastError());
   note_launches(1);

@@ -16,8 +16,8 @@ if [ "${MICRO:-1}" = "1" ]; then
 echo "== microbench"; timeout -s KILL 900 python tools/microbench.py --out gpurun_out/micro.json ${MICRO_ARGS:-} > gpurun_out/micro.log 2>&1; echo "micro rc=$?"; cat gpurun_out/micro.log | tail -20
 fi
 if [ "${NCU:-0}" = "1" ]; then
-echo "== ncu launch list"; timeout -s KILL 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:tc_linear -s 256 -c 256 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-graph --no-cpu-baseline --no-prefill > gpurun_out/ncu_bench.log 2>&1; echo "ncu rc=$?"
-echo "== ncu full decode"; timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:tc_linear -s 2 -c 1 -o gpurun_out/prof_decode_gate_up python tools/prof_decode.py gate_up 1 4 > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
+echo "== ncu launch list"; timeout -s KILL 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:decode_kernel -s 256 -c 256 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-graph --no-cpu-baseline --no-prefill > gpurun_out/ncu_bench.log 2>&1; echo "ncu rc=$?"
+echo "== ncu full decode"; timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:decode_kernel -s 2 -c 1 -o gpurun_out/prof_decode_gate_up python tools/prof_decode.py gate_up 1 4 > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
 echo "== ncu full gemm"; timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:tc_gemm -s 1 -c 1 -o gpurun_out/prof_gemm_gate_up python tools/gemm_bench.py --shapes gate_up --ms 4096 > gpurun_out/ncu_gemm.log 2>&1; echo "ncu gemm rc=$?"
 echo "== gemm bench"; timeout -s KILL 600 python tools/gemm_bench.py --out gpurun_out/gemm.json > gpurun_out/gemm.log 2>&1; tail -10 gpurun_out/gemm.log
 fi
