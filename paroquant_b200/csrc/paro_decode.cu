@@ -31,6 +31,11 @@
 
 namespace paro {
 
+#ifndef PARO_DEC_UNROLL
+#define PARO_DEC_UNROLL 4
+#endif
+constexpr int kDecUnroll = PARO_DEC_UNROLL;   // chunks of the dequant loop unrolled per trip (4 = straight-line)
+
 constexpr int kDecMaxStages = 24;
 constexpr int kDecTmemCols = 512;
 constexpr int kDecN = 16;            // MMA N: token rows, zero-padded (M_mma = 128 needs N % 16 == 0)
@@ -81,21 +86,20 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 
 // ---- prologue of one worker warp: groups gi = wi, wi + W, ... of the CTA's slice -> B operand rows
 // B[gi][k16 step s][k half h][row m][8 k]: 16 rows x 16 bytes per core-matrix pair, 512 bytes per step
+// (rows m >= M are the zero padding of the N = 16 MMA: zeroed once, by all worker warps, before griddepcontrol.wait)
 template <typename T, int ROWS>
 __device__ __forceinline__ void dec_write_b_rows(uint32_t xb_group, uint32_t rot, int M, int lane) {
-  for (int idx = lane; idx < 16 * kDecN; idx += 32) {
+  for (int idx = lane; idx < 16 * M; idx += 32) {
     const int m = idx >> 4, s = (idx >> 1) & 7, h = idx & 1;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (m < M) {
-      const int c0 = 16 * s + 8 * h;
-      if constexpr (ROWS == 1) {
-        v = lds128(rot + c0 * 2);
-      } else {
-        uint32_t e[8];
+    const int c0 = 16 * s + 8 * h;
+    uint4 v;
+    if constexpr (ROWS == 1) {
+      v = lds128(rot + c0 * 2);
+    } else {
+      uint32_t e[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) e[k] = lds16(rot + (c0 + k) * (ROWS * 2) + 2 * m);
-        v = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
-      }
+      for (int k = 0; k < 8; ++k) e[k] = lds16(rot + (c0 + k) * (ROWS * 2) + 2 * m);
+      v = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
     }
     sts128u(xb_group + s * (kDecN * 32) + h * (kDecN * 16) + (m >> 3) * 128 + (m & 7) * 16, v);
   }
@@ -130,6 +134,8 @@ __device__ __forceinline__ void dec_rotate_group(const DecParams &p, const DecRo
   if (p.krot == 8) {
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
+      // (keeping all 32 coefficients live across griddepcontrol.wait was tried: it spills at 80 registers and the
+      // stages get slower than with the MUFU work inline)
       float c0, s0, c1, s1;
       sincos2<T>(rm.tw[r], c0, s0, c1, s1);
       rotate_stage<T, ROWS>(rot, rm.idxw[r], c0, s0, c1, s1);
@@ -284,6 +290,9 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
     const int wi = warp, e = wi >> 2, q = warp & 3;
     const int L128 = 32 * q + lane;               // output column inside the 128-column block = TMEM lane
     const uint32_t lane_base = static_cast<uint32_t>(32 * q) << 16;
+    // zero padding rows of the B operand (all workers, before the wait: they do not depend on x)
+    for (int i = threadIdx.x; i < ng * (kDecN * 16); i += 32 * kWorkers) sts128u(xb + i * 16, make_uint4(0u, 0u, 0u, 0u));
+    named_bar_sync(1, 32 * kWorkers);   // the zeros are in place before any warp writes token rows
     DEC_TRACE(2);
     pdl_wait();  // x may have been written by the previous kernel
     DEC_TRACE(3);
@@ -320,7 +329,7 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
       if (use > 0) mbar_wait(bar_afree + 8 * e, (use - 1) & 1);  // the MMAs of my previous round have drained my A buffer
       tc_fence_after();
       const uint32_t wbase = rec + col_off;
-#pragma unroll
+#pragma unroll kDecUnroll
       for (int c = 0; c < 4; ++c) {
         const uint4 w4 = lds128(wbase + c * 256);
         uint32_t regs[16];

@@ -12,6 +12,16 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct"]
 
 
+EXTRA = ["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+         "sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed",
+         "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "smsp__mem_tensor_writes_op_stt.sum.pct_of_peak_sustained_elapsed",
+         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+         "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio", "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+         "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"]
+
+
 def raw(rep):
     out = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
@@ -24,7 +34,7 @@ def summarize(rep, title):
     for r in rows:
         lines.append(f"kernel: {r[hdr.index('Kernel Name')]}")
         for k in hdr:
-            if k in KEYS or "tensor" in k and "pct" in k:
+            if k in KEYS or k in EXTRA:
                 i = hdr.index(k)
                 lines.append(f"  {k:80s} {r[i]:>18s} {units[i]}")
     return "\n".join(lines) + "\n"
