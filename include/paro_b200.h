@@ -100,8 +100,9 @@ int paro_prepack(const paro_linear_shape *shape, const int32_t *qweight, const i
                  const void *theta, int32_t theta_dtype, const void *channel_scales,
                  int32_t cs_dtype, void *packed, paro_stream_t stream);
 
-/* Bytes of scratch paro_linear_forward needs for up to max_m rows.  The caller zero-fills it
- * once after allocation; the kernels leave it zeroed again after every launch.          */
+/* Bytes of scratch paro_linear_forward needs for up to max_m rows: the rotated activations
+ * of the M > 16 path (n_parts x M x K elements).  The M <= 16 kernel reduces its K slices
+ * through distributed shared memory and uses none; at least 256 is returned.            */
 size_t paro_workspace_bytes(const paro_linear_shape *shape, int64_t max_m);
 
 /* y[M, N] = rotate_p(x) . dequant(W)[:, part p] for every partition p (+ bias) in ONE call.
@@ -109,7 +110,7 @@ size_t paro_workspace_bytes(const paro_linear_shape *shape, int64_t max_m);
  *   x          device [M, K] of shape->dtype, contiguous
  *   bias       device [N] of shape->dtype or NULL
  *   y          device [M, N] of shape->dtype
- *   workspace  device, >= paro_workspace_bytes(shape, M), zeroed before first use
+ *   workspace  device, >= paro_workspace_bytes(shape, M), 256-byte aligned
  * M <= 16 runs the fused rotate+dequant+GEMV kernel (HBM-bound); larger M the
  * rotate + tcgen05 GEMM path.                                                            */
 int paro_linear_forward(const paro_linear_shape *shape, const void *packed, const void *x,
