@@ -84,24 +84,31 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
 }
 
-// ---- prologue of one worker warp: groups gi = wi, wi + W, ... of the CTA's slice -> B operand rows
-// B[gi][k16 step s][k half h][row m][8 k]: 16 rows x 16 bytes per core-matrix pair, 512 bytes per step
-// (rows m >= M are the zero padding of the N = 16 MMA: zeroed once, by all worker warps, before griddepcontrol.wait)
+// ---- prologue.  A rotation TASK = (group gi of the CTA's slice, block of up to ROWS <= 4 token rows); worker warp w takes
+// tasks w, w + W, ...  (M = 16: four tasks per group, so all warps share the rotation instead of 16-row tiles on a few).
+// B[gi][k16 step s][k half h][row m][8 k]: 16 rows x 16 bytes per core-matrix pair, 512 bytes per step.
 template <typename T, int ROWS>
-__device__ __forceinline__ void dec_write_b_rows(uint32_t xb_group, uint32_t rot, int M, int lane) {
-  for (int idx = lane; idx < 16 * M; idx += 32) {
-    const int m = idx >> 4, s = (idx >> 1) & 7, h = idx & 1;
-    const int c0 = 16 * s + 8 * h;
+__device__ __forceinline__ void dec_write_b_rows(uint32_t xb_group, uint32_t rot, int m0, int nrows, int lane) {
+  for (int idx = lane; idx < 16 * nrows; idx += 32) {
+    const int ml = idx >> 4, s = (idx >> 1) & 7, h = idx & 1;
+    const int c0 = 16 * s + 8 * h, m = m0 + ml;
     uint4 v;
     if constexpr (ROWS == 1) {
       v = lds128(rot + c0 * 2);
     } else {
       uint32_t e[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) e[k] = lds16(rot + (c0 + k) * (ROWS * 2) + 2 * m);
+      for (int k = 0; k < 8; ++k) e[k] = lds16(rot + (c0 + k) * (ROWS * 2) + 2 * ml);
       v = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
     }
     sts128u(xb_group + s * (kDecN * 32) + h * (kDecN * 16) + (m >> 3) * 128 + (m & 7) * 16, v);
+  }
+}
+// rows [M, 16) of a group are the zero padding of the N = 16 MMA
+__device__ __forceinline__ void dec_zero_b_rows(uint32_t xb_group, int M, int lane) {
+  for (int idx = lane; idx < 16 * (kDecN - M); idx += 32) {
+    const int m = M + (idx >> 4), s = (idx >> 1) & 7, h = idx & 1;
+    sts128u(xb_group + s * (kDecN * 32) + h * (kDecN * 16) + (m >> 3) * 128 + (m & 7) * 16, make_uint4(0u, 0u, 0u, 0u));
   }
 }
 
@@ -124,10 +131,11 @@ __device__ __forceinline__ void dec_fetch_meta(const DecParams &p, int part, int
 }
 
 template <typename T, int ROWS>
-__device__ __forceinline__ void dec_rotate_group(const DecParams &p, const DecRotMeta &rm, int gk, int lane, uint32_t rot, uint32_t xb_group,
-                                                 long long t_entry) {
+__device__ __forceinline__ void dec_rotate_task(const DecParams &p, const DecRotMeta &rm, int gk, int m0, int lane, uint32_t rot, uint32_t xb_group,
+                                                long long t_entry) {
   uint2 raw[ROWS];
-  load_x<T, ROWS>(p, gk, lane, raw);
+  load_x<T, ROWS>(p, gk, lane, raw, m0);
+  if (m0 == 0) dec_zero_b_rows(xb_group, p.M, lane);   // while the loads are in flight
   scale_and_stage<T, ROWS>(rot, lane, raw, rm.csw);
   __syncwarp();
   if (p.trace && threadIdx.x == 0 && blockIdx.x < kDecTraceCtas) g_dec_trace[blockIdx.x * kDecTraceSlots + 0] = clock64() - t_entry;
@@ -153,16 +161,19 @@ __device__ __forceinline__ void dec_rotate_group(const DecParams &p, const DecRo
     }
   }
   if (p.trace && threadIdx.x == 0 && blockIdx.x < kDecTraceCtas) g_dec_trace[blockIdx.x * kDecTraceSlots + 9] = clock64() - t_entry;
-  dec_write_b_rows<T, ROWS>(xb_group, rot, p.M, lane);
+  const int left = p.M - m0;
+  dec_write_b_rows<T, ROWS>(xb_group, rot, m0, left < ROWS ? left : ROWS, lane);
   __syncwarp();
 }
 
+// tasks t = wi, wi + nwarps, ... of ng * nq (nq row blocks per group); the first task's metadata was fetched before the wait
 template <typename T, int ROWS>
-__device__ __forceinline__ void dec_prologue(const DecParams &p, DecRotMeta &rm, int part, int g_begin, int ng, int wi, int nworkers,
+__device__ __forceinline__ void dec_prologue(const DecParams &p, DecRotMeta &rm, int part, int g_begin, int ntasks, int nq, int wi, int nwarps,
                                              int lane, uint32_t rot, uint32_t xb, long long t_entry) {
-  for (int gi = wi; gi < ng; gi += nworkers) {
-    if (gi != wi) dec_fetch_meta(p, part, g_begin + gi, lane, rm);   // the first group's metadata was fetched before the wait
-    dec_rotate_group<T, ROWS>(p, rm, g_begin + gi, lane, rot, xb + gi * (kDecN * 256), t_entry);
+  for (int t = wi; t < ntasks; t += nwarps) {
+    const int gi = t / nq, rq = t - gi * nq;
+    if (t != wi) dec_fetch_meta(p, part, g_begin + gi, lane, rm);
+    dec_rotate_task<T, ROWS>(p, rm, g_begin + gi, rq * ROWS, lane, rot, xb + gi * (kDecN * 256), t_entry);
   }
 }
 
@@ -209,7 +220,9 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
   const uint8_t *rec0 = p.packed + p.rec_off + (static_cast<size_t>(p.part_block_begin[part] + cb_begin) * p.groups + g_begin) * kBlockBytes;
 
   DecRotMeta rm;
-  if (warp < kWorkers && warp < ng) dec_fetch_meta(p, part, g_begin + warp, lane, rm);   // flies during the barrier init / TMEM allocation
+  const int nq = p.M > 4 ? (p.M + 3) >> 2 : 1, ntasks = ng * nq;   // rotation tasks: row blocks of 4 for M > 4
+  if (warp < kWorkers && warp < ntasks && warp < p.rot_warps)
+    dec_fetch_meta(p, part, g_begin + warp / nq, lane, rm);   // flies during the barrier init / TMEM allocation
 
   if (warp == kWorkers) {
     // one barrier per lane
@@ -290,20 +303,15 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
     const int wi = warp, e = wi >> 2, q = warp & 3;
     const int L128 = 32 * q + lane;               // output column inside the 128-column block = TMEM lane
     const uint32_t lane_base = static_cast<uint32_t>(32 * q) << 16;
-    // zero padding rows of the B operand (all workers, before the wait: they do not depend on x)
-    for (int i = threadIdx.x; i < ng * (kDecN * 16); i += 32 * kWorkers) sts128u(xb + i * 16, make_uint4(0u, 0u, 0u, 0u));
-    named_bar_sync(1, 32 * kWorkers);   // the zeros are in place before any warp writes token rows
     DEC_TRACE(2);
     pdl_wait();  // x may have been written by the previous kernel
     DEC_TRACE(3);
-    if (wi < ng && wi < p.rot_warps) {
+    if (wi < ntasks && wi < p.rot_warps) {
       const uint32_t rot = smem0 + p.rot_off + wi * p.rot_bytes;
       const int M = p.M, rw = p.rot_warps;
-      if (M == 1) dec_prologue<T, 1>(p, rm, part, g_begin, ng, wi, rw, lane, rot, xb, t_entry);
-      else if (M == 2) dec_prologue<T, 2>(p, rm, part, g_begin, ng, wi, rw, lane, rot, xb, t_entry);
-      else if (M <= 4) dec_prologue<T, 4>(p, rm, part, g_begin, ng, wi, rw, lane, rot, xb, t_entry);
-      else if (M <= 8) dec_prologue<T, 8>(p, rm, part, g_begin, ng, wi, rw, lane, rot, xb, t_entry);
-      else dec_prologue<T, 16>(p, rm, part, g_begin, ng, wi, rw, lane, rot, xb, t_entry);
+      if (M == 1) dec_prologue<T, 1>(p, rm, part, g_begin, ntasks, nq, wi, rw, lane, rot, xb, t_entry);
+      else if (M == 2) dec_prologue<T, 2>(p, rm, part, g_begin, ntasks, nq, wi, rw, lane, rot, xb, t_entry);
+      else dec_prologue<T, 4>(p, rm, part, g_begin, ntasks, nq, wi, rw, lane, rot, xb, t_entry);
       fence_proxy_async_smem();  // B rows were written through the generic proxy, tcgen05.mma reads them through the async proxy
     }
     __syncwarp();
@@ -506,7 +514,8 @@ static bool dec_carve_with(const DecPlan &plan, int M, int rot_bytes, int sets, 
 
 // every group gets its own rotating warp when the tiles fit; otherwise fewer warps take several groups each
 static bool dec_carve(const DecPlan &plan, int M, int rot_bytes, int sets, DecSmem &s) {
-  int rw = plan.ng_max < 4 * sets ? plan.ng_max : 4 * sets;
+  const int ntasks = plan.ng_max * (M > 4 ? (M + 3) / 4 : 1);
+  int rw = ntasks < 4 * sets ? ntasks : 4 * sets;
   for (;;) {
     if (dec_carve_with(plan, M, rot_bytes, sets, rw, s)) return true;
     if (rw <= 2) return false;
@@ -570,7 +579,7 @@ static int launch_decode(DecParams &p, const Layout &L, int sms, cudaStream_t st
     }
     plan.grid = plan.ranges * c;
     // critical path in rounds: main loop of the busiest CTA + rotation passes + a small charge per doubling of the cluster
-    const int passes = (plan.ng_max + 4 * SETS - 1) / (4 * SETS);
+    const int passes = (plan.ng_max * (p.M > 4 ? (p.M + 3) / 4 : 1) + 4 * SETS - 1) / (4 * SETS);
     const long cost = static_cast<long>(plan.nj_max) * plan.ng_max * 8 + passes * 24 + cs * 2;
     if (best_cost < 0 || cost < best_cost) { best = plan; best_s = s; best_cost = cost; }
   }
@@ -623,7 +632,7 @@ int decode_forward(const paro_linear_shape &s, const Layout &L, const void *pack
   p.x = x; p.y = y; p.bias = bias;
   p.M = static_cast<int>(M); p.K = L.K; p.N = L.N;
   p.n_parts = L.n_parts; p.groups = L.groups; p.krot = L.krot;
-  p.rot_bytes = kGroup * 2 * (M == 1 ? 1 : M == 2 ? 2 : M <= 4 ? 4 : M <= 8 ? 8 : 16);
+  p.rot_bytes = kGroup * 2 * (M == 1 ? 1 : M == 2 ? 2 : 4);   // rotation tile of one task: 128 channels x up to 4 rows
   p.trace = dec_env_int("PARO_DECODE_TRACE", 0);
   for (int i = 0; i <= PARO_MAX_PARTS; ++i) {
     p.part_col_begin[i] = L.part_col_begin[i];
