@@ -104,14 +104,6 @@ __device__ __forceinline__ void dec_write_b_rows(uint32_t xb_group, uint32_t rot
     sts128u(xb_group + s * (kDecN * 32) + h * (kDecN * 16) + (m >> 3) * 128 + (m & 7) * 16, v);
   }
 }
-// rows [M, 16) of a group are the zero padding of the N = 16 MMA
-__device__ __forceinline__ void dec_zero_b_rows(uint32_t xb_group, int M, int lane) {
-  for (int idx = lane; idx < 16 * (kDecN - M); idx += 32) {
-    const int m = M + (idx >> 4), s = (idx >> 1) & 7, h = idx & 1;
-    sts128u(xb_group + s * (kDecN * 32) + h * (kDecN * 16) + (m >> 3) * 128 + (m & 7) * 16, make_uint4(0u, 0u, 0u, 0u));
-  }
-}
-
 struct DecRotMeta {
   uint32_t idxw[8], tw[8];
   uint2 csw;
@@ -135,7 +127,6 @@ __device__ __forceinline__ void dec_rotate_task(const DecParams &p, const DecRot
                                                 long long t_entry) {
   uint2 raw[ROWS];
   load_x<T, ROWS>(p, gk, lane, raw, m0);
-  if (m0 == 0) dec_zero_b_rows(xb_group, p.M, lane);   // while the loads are in flight
   scale_and_stage<T, ROWS>(rot, lane, raw, rm.csw);
   __syncwarp();
   if (p.trace && threadIdx.x == 0 && blockIdx.x < kDecTraceCtas) g_dec_trace[blockIdx.x * kDecTraceSlots + 0] = clock64() - t_entry;
@@ -303,6 +294,12 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
     const int wi = warp, e = wi >> 2, q = warp & 3;
     const int L128 = 32 * q + lane;               // output column inside the 128-column block = TMEM lane
     const uint32_t lane_base = static_cast<uint32_t>(32 * q) << 16;
+    // rows [M, 16) of every group are the zero padding of the N = 16 MMA: all workers clear the B operand before the
+    // dependency wait (it does not depend on x); the rotation tasks then write only token rows
+    if (p.M < kDecN) {
+      for (int i = threadIdx.x; i < ng * (kDecN * 16); i += 32 * kWorkers) sts128u(xb + i * 16, make_uint4(0u, 0u, 0u, 0u));
+      named_bar_sync(1, 32 * kWorkers);
+    }
     DEC_TRACE(2);
     pdl_wait();  // x may have been written by the previous kernel
     DEC_TRACE(3);
