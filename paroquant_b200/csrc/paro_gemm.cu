@@ -11,13 +11,12 @@
 //   D  = fp32 [128 x NT] in TMEM (NT <= 256 columns), one rounding to T in the epilogue, bias in T.
 //
 // CTA = one (128-column block of N) x (NT-token block of M) output tile over the whole K.
-// Warp roles as in paro_tc.cu: warp 0 TMA producer (one 8576-byte weight record + 2 B stages per
+// Warp roles as in paro_decode.cu: warp 0 TMA producer (one 8576-byte weight record + 2 B stages per
 // round), warp 1 TMEM allocator + single-thread tcgen05.mma issuer, warps 2-17 four dequant sets
 // (thread = one output column; round r -> set r % 4, each set owns one A buffer), all of them read D back.
 // At NT = 256 one round is 8 MMAs x 128 cycles on the tensor pipe against ~260 dequant
 // instructions per worker thread: the CUDA cores idle, the tensor core does not.
-#include "paro_common.cuh"
-#include "paro_layout.h"
+#include "paro_tc_common.cuh"
 
 namespace paro {
 
@@ -42,94 +41,6 @@ struct GemmParams {
   int part_col_begin[PARO_MAX_PARTS + 1];
   int part_block_begin[PARO_MAX_PARTS + 1];
   long long rec_off, xr_part_stride;
-};
-
-// ---- tcgen05 / mbarrier wrappers (same forms as paro_tc.cu)
-__device__ __forceinline__ void g_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void g_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void g_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void g_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void g_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void g_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
-      : "memory");
-}
-__device__ __forceinline__ void g_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void g_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ uint64_t g_desc_kmajor(uint32_t addr, uint32_t lbo, uint32_t sbo) {
-  return static_cast<uint64_t>((addr >> 4) & 0x3FFF) | (static_cast<uint64_t>((lbo >> 4) & 0x3FFF) << 16) |
-         (static_cast<uint64_t>((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
-}
-template <typename T> __device__ __forceinline__ uint32_t g_instr_desc(int n) {
-  const uint32_t fmt = Traits<T>::code == PARO_BF16 ? 1u : 0u;
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (8u << 24);
-}
-__device__ __forceinline__ uint32_t g_lds8(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ bool g_elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ uint32_t g_and_or(uint32_t a, uint32_t mask, uint32_t magic) {
-  uint32_t d;
-  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(mask), "r"(magic));
-  return d;
-}
-
-// one row's dequant, as in paro_tc.cu
-template <typename T> struct GRowDequant;
-template <> struct GRowDequant<__nv_bfloat16> {
-  uint32_t s2, z2;
-  __device__ __forceinline__ void prep(uint32_t s_bits, uint32_t z) {
-    s2 = s_bits * 0x00010001u;
-    z2 = (0x4300u | z) * 0x00010001u;
-  }
-  __device__ __forceinline__ uint32_t one(uint32_t w) const {
-    const __nv_bfloat162 d = __hsub2(unpack2<__nv_bfloat16>(g_and_or(w, 0x000F000Fu, 0x43004300u)), unpack2<__nv_bfloat16>(z2));
-    return pack2<__nv_bfloat16>(__hmul2(d, unpack2<__nv_bfloat16>(s2)));
-  }
-  __device__ __forceinline__ void word(uint32_t w, uint32_t *r) const {
-    r[0] = one(w); r[1] = one(w >> 4); r[2] = one(w >> 8); r[3] = one(w >> 12);
-  }
-};
-template <> struct GRowDequant<__half> {
-  uint32_t s2, z_lo, z_hi16;
-  __device__ __forceinline__ void prep(uint32_t s_bits, uint32_t z) {
-    s2 = s_bits * 0x00010001u;
-    z_lo = (0x6400u | z) * 0x00010001u;
-    z_hi16 = (0xD400u | (z << 4)) * 0x00010001u;
-  }
-  __device__ __forceinline__ void word(uint32_t w, uint32_t *r) const {
-    const uint32_t w8 = w >> 8;
-    const __half2 sixteenth = unpack2<__half>(0x2C002C00u), s = unpack2<__half>(s2);
-    r[0] = pack2<__half>(__hmul2(__hsub2(unpack2<__half>(g_and_or(w, 0x000F000Fu, 0x64006400u)), unpack2<__half>(z_lo)), s));
-    r[1] = pack2<__half>(__hmul2(__hfma2(unpack2<__half>(g_and_or(w, 0x00F000F0u, 0x64006400u)), sixteenth, unpack2<__half>(z_hi16)), s));
-    r[2] = pack2<__half>(__hmul2(__hsub2(unpack2<__half>(g_and_or(w8, 0x000F000Fu, 0x64006400u)), unpack2<__half>(z_lo)), s));
-    r[3] = pack2<__half>(__hmul2(__hfma2(unpack2<__half>(g_and_or(w8, 0x00F000F0u, 0x64006400u)), sixteenth, unpack2<__half>(z_hi16)), s));
-  }
 };
 
 template <typename T>
@@ -161,9 +72,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const GemmPara
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kGemmTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  g_fence_before();
+  tc_fence_before();
   __syncthreads();
-  g_fence_after();
+  tc_fence_after();
   const uint32_t tmem = lds32(tmem_slot);
   const uint32_t d_col0 = 64 * kABufs;
 
@@ -202,27 +113,27 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const GemmPara
     // region ptxas keeps descriptors in uniform registers; a plain `lane == 0` branch wraps every tcgen05.mma
     // in a divergence loop and the issuing thread, not the tensor pipe, becomes the limit at small NT)
     {
-      const uint32_t idesc = g_instr_desc<T>(NT);
+      const uint32_t idesc = instr_desc<T>(NT);
       const uint32_t step_bytes = NT * 32, lbo = NT * 16;
-      const uint64_t desc_hi = g_desc_kmajor(0, lbo, 128);
+      const uint64_t desc_hi = smem_desc_kmajor(0, lbo, 128);
       int abuf = 0, a_use = 0;   // A buffer of round r = its dequant set = r % kGemmSets, r / kGemmSets earlier uses
       for (int r = 0; r < rounds; ++r) {
         mbar_wait(bar_afull + 8 * abuf, a_use & 1);
         for (int hstage = 0; hstage < 2; ++hstage) {
           const int bi = 2 * r + hstage, bs = bi % kBStages;
           mbar_wait(bar_bfull + 8 * bs, (bi / kBStages) & 1);
-          g_fence_after();
+          tc_fence_after();
           const uint64_t bdesc0 = desc_hi | static_cast<uint64_t>(((b_ring + bs * b_stage_bytes) >> 4) & 0x3FFF);
-          if (g_elect_one()) {
+          if (elect_one()) {
 #pragma unroll
             for (int s4 = 0; s4 < 4; ++s4) {
               const int s = hstage * 4 + s4;
-              g_mma_ts(tmem + d_col0, tmem + abuf * 64 + 8 * s, bdesc0 + s4 * (step_bytes >> 4), idesc, (r | s) ? 1u : 0u);
+              tc_mma_ts(tmem + d_col0, tmem + abuf * 64 + 8 * s, bdesc0 + s4 * (step_bytes >> 4), idesc, (r | s) ? 1u : 0u);
             }
-            g_commit(bar_bempty + 8 * bs);
+            tc_commit(bar_bempty + 8 * bs);
             if (hstage == 1) {
-              g_commit(bar_afree + 8 * abuf);
-              if (r == rounds - 1) g_commit(bar_dfull);
+              tc_commit(bar_afree + 8 * abuf);
+              if (r == rounds - 1) tc_commit(bar_dfull);
             }
           }
           __syncwarp();
@@ -245,10 +156,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const GemmPara
       const int ws = r % kWStages;
       mbar_wait(bar_wfull + 8 * ws, (r / kWStages) & 1);
       const uint32_t rec = w_ring + ws * kWStage;
-      GRowDequant<T> dq;
-      dq.prep(lds16(rec + kBlockScaleOff + 2 * L128), g_lds8(rec + kBlockZeroOff + L128));   // zero-filled past the partition's end
+      RowDequant<T> dq;
+      dq.prep(lds16(rec + kBlockScaleOff + 2 * L128), lds8(rec + kBlockZeroOff + L128));   // zero-filled past the partition's end
       if (use > 0) mbar_wait(bar_afree + 8 * e, (use - 1) & 1);
-      g_fence_after();
+      tc_fence_after();
       const uint32_t wbase = rec + col_off;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -258,10 +169,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const GemmPara
         dq.word(w4.y, regs + 4);
         dq.word(w4.z, regs + 8);
         dq.word(w4.w, regs + 12);
-        g_st16(ta + 16 * c, regs);
+        tc_st16(ta + 16 * c, regs);
       }
-      g_wait_st();
-      g_fence_before();
+      tc_wait_st();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(bar_afull + 8 * e);
@@ -272,7 +183,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const GemmPara
 
     // ---- epilogue: set e converts its share of the token columns of its lanes
     mbar_wait(bar_dfull, 0);
-    g_fence_after();
+    tc_fence_after();
     const int n = n0 + L128;
     const bool n_ok = n < n_end;
     float bias_f = 0.f;
@@ -282,8 +193,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const GemmPara
     const int set_cols = NT / kGemmSets >= 16 ? NT / kGemmSets : 16;   // token columns this set converts
     for (int c0 = e * set_cols; c0 < (e + 1) * set_cols && c0 < NT; c0 += 16) {
       uint32_t v[16];
-      g_ld16(tmem + lane_base + d_col0 + c0, v);
-      g_wait_ld();
+      tc_ld16(tmem + lane_base + d_col0 + c0, v);
+      tc_wait_ld();
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         const int64_t m = static_cast<int64_t>(tb) * NT + c0 + k;
@@ -297,10 +208,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const GemmPara
   }
 
   __syncwarp();
-  g_fence_before();
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    g_fence_after();
+    tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kGemmTmemCols) : "memory");
   }
 }

@@ -1,4 +1,4 @@
-// Device helpers shared by the small-M tensor-core kernels (paro_tc.cu, paro_decode.cu):
+// Device helpers shared by the tensor-core kernels (paro_decode.cu, paro_gemm.cu):
 // tcgen05 / TMEM wrappers, UMMA descriptors, cluster + DSMEM primitives, the INT4 -> T row dequant
 // and the in-warp pairwise rotation (rounding points of /root/reference/paroquant/kernels/cuda/rotation.cuh:91-173).
 #pragma once
@@ -40,6 +40,21 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16])
 __device__ __forceinline__ void tc_ld2(uint32_t taddr, uint32_t &a, uint32_t &b) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
 // K-major, no swizzle: 8-row x 16-byte core matrices; `lbo` = byte distance between the two k-halves
 // of a k16 step, `sbo` = byte distance between 8-row groups (cute::UMMA::SmemDescriptor, version 1)
 __device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t addr, uint32_t lbo, uint32_t sbo) {

@@ -44,9 +44,10 @@ def test_prepack_preserves_operand_bit_exact(PK, oracle, dt, K, parts):
 
 @pytest.mark.parametrize("dt", ["bfloat16", "float16"])
 @pytest.mark.parametrize("K,parts,Ms", [
-    (512, [64], (1, 2, 3, 8, 9, 16)),                 # one K-slice: direct store path
-    (1024, [256, 128], (1, 4, 7, 16)),                # 2 slices, merged, different rotation per partition
-    (640, [48, 16, 32], (1, 5, 16)),                  # ragged: last slice has 1 group, odd tile counts
+    (512, [64], (1, 2, 3, 8, 9, 16)),                 # one partial 128-column block
+    (1024, [256, 128], (1, 4, 7, 16)),                # merged, different rotation per partition
+    (640, [48, 16, 32], (1, 5, 16)),                  # every partition is a partial block, 5 groups over the cluster's K slices
+    (256, [272, 16], (3, 12)),                        # two full blocks + a partial one; 12 rows = three rotation row blocks
     (4096, [4096], (1, 4, 16)),                       # BASELINE config 0/1 shape
 ])
 def test_fused_linear_vs_oracle(PK, oracle, dt, K, parts, Ms):
@@ -187,11 +188,12 @@ def test_vs_reference_pipeline_fixture(PK, path):
 
 @pytest.mark.parametrize("dt", ["bfloat16", "float16"])
 @pytest.mark.parametrize("K,parts,M", [(512, [128], 17), (1024, [256, 128], 40), (1024, [256, 128], 64), (4096, [1024], 100),
-                                       (4096, [4096], 256), (4096, [4096, 1024, 1024], 300), (11008, [512], 33), (14336, [256], 257)])
+                                       (4096, [4096], 256), (4096, [4096, 1024, 1024], 300), (11008, [512], 33), (14336, [256], 257),
+                                       (1152, [128], 40), (256, [272, 16], 33)])
 def test_large_m_gemm_vs_rotate_and_dense(PK, dt, K, parts, M):
     """M > 16: rotation pre-pass + tcgen05 GEMM against fp64 matmul on the kernel's own dequantised operand and the
     standalone rotate kernel (both bit-checked elsewhere); ragged M (not a multiple of the token tile), merged
-    projections, ragged K-slices, partial 128-column blocks."""
+    projections, K longer than the weight ring (stage reuse), partial 128-column blocks."""
     import paroquant_b200.kernels.cuda  # noqa: F401
     L = make_synthetic_layer(K, parts, seed=53, device="cuda", bias=(M == 40))
     k = PK.from_buffers(L, _TD[dt], max_m=M)
