@@ -1,5 +1,5 @@
-// Fused small-M path, second generation (M <= 16): scaled pairwise rotation of x + INT4 group dequant
-// + GEMV/GEMM in ONE launch per (merged) linear, ONE persistent CTA per SM.  Replaces the reference's
+// Fused small-M path (M <= 16): scaled pairwise rotation of x + INT4 group dequant + GEMV/GEMM in ONE
+// launch per (merged) linear, ONE persistent CTA per SM.  Replaces the reference's
 // rotate -> Marlin kernel pairs (/root/reference/paroquant/inference/backends/vllm/plugin.py:281-311).
 //
 // Formulation (operand-swapped, as the large-M kernel): D[n, m] += W[n, k] * x_rot[m, k]
@@ -17,8 +17,9 @@
 // memory to rank (block mod c); one cluster barrier; fixed summation order (bit-reproducible).
 //
 // Roles (SETS x 4 dequant warps + 2): warps 0..4*SETS-1 workers (TMEM lane quarter = warp % 4): the
-// prologue rotates the slice's groups (one group per warp, __syncwarp only); the main loop takes rounds
-// r = set, set + SETS, ...; the set that dequantised a block's last group reads D back.  Warp 4*SETS:
+// prologue rotates the slice's groups (tasks of one group x up to 4 token rows per warp, __syncwarp only);
+// the main loop takes rounds r = set, set + SETS, ...; the set that dequantised a block's last group reads
+// D back.  Warp 4*SETS:
 // TMA producer (ONE 8576-byte record = weights + scales + zeros of a round per cp.async.bulk, into an
 // mbarrier ring, issued before griddepcontrol.wait).  Warp 4*SETS+1: TMEM allocator + tcgen05.mma issuer
 // (one elected lane).
@@ -60,7 +61,7 @@ struct DecParams {
   int M, K, N;
   int n_parts, groups, krot;
   int c, c_shift;                 // cluster size (K slices of this launch), log2
-  int nstages, rot_bytes, rot_warps, trace;   // rot_warps: worker warps that rotate (one group each per pass)
+  int nstages, rot_bytes, rot_warps, trace;   // rot_warps: worker warps that take rotation tasks (each owns one rot_bytes tile)
   int xb_off, rot_off, recv_off, bar_off;   // shared-memory carve-up (bytes)
   int part_col_begin[PARO_MAX_PARTS + 1];
   int part_block_begin[PARO_MAX_PARTS + 1];
