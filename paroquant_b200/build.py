@@ -42,7 +42,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     for src in sources():
         obj = objdir / (src.stem + ".o")
         if force or _stale(obj, [src] + headers):
-            cmd = [NVCC, *FLAGS, "-c", str(src), "-o", str(obj)]
+            cmd = [NVCC, *FLAGS, *os.environ.get("PARO_EXTRA_NVCC_FLAGS", "").split(), "-c", str(src), "-o", str(obj)]   # e.g. -DPARO_DEC_HALF=1
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             jobs.append((src, cmd))
