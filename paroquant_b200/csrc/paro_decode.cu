@@ -37,15 +37,6 @@ namespace paro {
 #endif
 constexpr int kDecUnroll = PARO_DEC_UNROLL;   // chunks of the dequant loop unrolled per trip (4 = straight-line)
 
-// EXPERIMENT (build with -DPARO_DEC_HALF=1; not the shipped configuration, not yet measured): hand the A operand to the
-// tensor core in two halves of 64 channels, each with its own full/free barriers.  The ncu source view of the shipped
-// kernel shows ~39 % of the dequant warps' samples on the wait for their own previous round's MMAs (one A buffer per
-// set, TMEM has no room for two); with halves a set refills half 0 while the MMAs of half 1 are in flight.
-#ifndef PARO_DEC_HALF
-#define PARO_DEC_HALF 0
-#endif
-constexpr int kDecHalves = PARO_DEC_HALF ? 2 : 1;
-
 constexpr int kDecMaxStages = 24;
 constexpr int kDecTmemCols = 512;
 constexpr int kDecN = 16;            // MMA N: token rows, zero-padded (M_mma = 128 needs N % 16 == 0)
@@ -181,8 +172,8 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
   const uint32_t smem0 = smem_u32(smem);
   const uint32_t xb = smem0 + p.xb_off, recv = smem0 + p.recv_off, bars = smem0 + p.bar_off;
   const uint32_t bar_wfull = bars, bar_wempty = bars + 8 * kDecMaxStages;
-  const uint32_t bar_afull = bars + 16 * kDecMaxStages, bar_afree = bar_afull + 64 * kDecHalves;   // [set][half]
-  const uint32_t bar_dfull = bar_afull + 128 * kDecHalves, bar_dfree = bar_dfull + 64, bar_xb = bar_dfull + 80, tmem_slot = bar_dfull + 88;
+  const uint32_t bar_afull = bars + 16 * kDecMaxStages, bar_afree = bar_afull + 64;
+  const uint32_t bar_dfull = bar_afull + 128, bar_dfree = bar_afull + 192, bar_xb = bar_afull + 208, tmem_slot = bar_afull + 216;
   constexpr uint32_t d_col0 = 64 * SETS;
 
   // ---- my range of 128-column blocks (within one partition) and my K-slice (whole groups, ragged)
@@ -220,10 +211,8 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
     // on the stale phase): A-buffer and D-ready barriers are per dequant set, ring stages are always consumed by the
     // same set (stage count is a multiple of SETS), the producer / MMA lanes wait sequentially on the rest.
     if (lane < SETS) {
-      for (int h = 0; h < kDecHalves; ++h) {
-        mbar_init(bar_afull + 8 * (kDecHalves * lane + h), 4);
-        mbar_init(bar_afree + 8 * (kDecHalves * lane + h), 1);
-      }
+      mbar_init(bar_afull + 8 * lane, 4);
+      mbar_init(bar_afree + 8 * lane, 1);
       mbar_init(bar_dfull + 8 * lane, 1);
     }
     if (lane < 2) mbar_init(bar_dfree + 8 * lane, 4);
@@ -272,21 +261,17 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
 #pragma unroll 1
     for (int r = 0; r < nrounds; ++r) {
       if (gi == 0 && j >= 2) mbar_wait(bar_dfree + 8 * (j & 1), ((j >> 1) - 1) & 1);   // D buffer read back by its previous user
+      mbar_wait(bar_afull + 8 * set, use & 1);
+      tc_fence_after();
       const uint32_t td = tmem + d_col0 + (j & 1) * kDecN, ta = tmem + set * 64;
       const uint64_t bdesc0 = desc_hi | static_cast<uint64_t>(((xb + gi * (kDecN * 256)) >> 4) & 0x3FFF);
+      if (elect_one()) {
 #pragma unroll
-      for (int h = 0; h < kDecHalves; ++h) {
-        mbar_wait(bar_afull + 8 * (kDecHalves * set + h), use & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          constexpr int kSteps = 8 / kDecHalves;
-#pragma unroll
-          for (int s = h * kSteps; s < (h + 1) * kSteps; ++s) tc_mma_ts(td, ta + 8 * s, bdesc0 + s * ((kDecN * 32) >> 4), idesc, (gi | s) ? 1u : 0u);
-          tc_commit(bar_afree + 8 * (kDecHalves * set + h));
-          if (h == kDecHalves - 1 && gi == ng - 1) tc_commit(bar_dfull + 8 * set);   // the set that dequantised the block's last group reads D back
-        }
-        __syncwarp();
+        for (int s = 0; s < 8; ++s) tc_mma_ts(td, ta + 8 * s, bdesc0 + s * ((kDecN * 32) >> 4), idesc, (gi | s) ? 1u : 0u);
+        tc_commit(bar_afree + 8 * set);
+        if (gi == ng - 1) tc_commit(bar_dfull + 8 * set);   // the set that dequantised the block's last group reads D back
       }
+      __syncwarp();
       if (++set == SETS) { set = 0; ++use; }
       if (++gi == ng) { gi = 0; ++j; }
     }
@@ -332,33 +317,9 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
       const uint32_t rec = smem0 + st * kDecStage;
       RowDequant<T> dq;
       dq.prep(lds16(rec + kBlockScaleOff + 2 * L128), lds8(rec + kBlockZeroOff + L128));
-      const uint32_t wbase = rec + col_off;
-#if PARO_DEC_HALF
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (use > 0) mbar_wait(bar_afree + 8 * (2 * e + h), (use - 1) & 1);  // the MMAs of my previous round have drained this half
-        tc_fence_after();
-#pragma unroll
-        for (int c = 2 * h; c < 2 * h + 2; ++c) {
-          const uint4 w4 = lds128(wbase + c * 256);
-          uint32_t regs[16];
-          dq.word(w4.x, regs + 0);
-          dq.word(w4.y, regs + 4);
-          dq.word(w4.z, regs + 8);
-          dq.word(w4.w, regs + 12);
-          tc_st16(ta + 16 * c, regs);
-        }
-        tc_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (h == 0 && lane == 0) mbar_arrive(bar_afull + 8 * (2 * e));
-      }
-      if (lane == 0) {
-        mbar_arrive(bar_afull + 8 * (2 * e + 1));
-        mbar_arrive(bar_wempty + 8 * st);
-#else
       if (use > 0) mbar_wait(bar_afree + 8 * e, (use - 1) & 1);  // the MMAs of my previous round have drained my A buffer
       tc_fence_after();
+      const uint32_t wbase = rec + col_off;
 #pragma unroll kDecUnroll
       for (int c = 0; c < 4; ++c) {
         const uint4 w4 = lds128(wbase + c * 256);
@@ -375,7 +336,6 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
       if (lane == 0) {
         mbar_arrive(bar_afull + 8 * e);
         mbar_arrive(bar_wempty + 8 * st);
-#endif
         if (p.trace && q == 0 && blockIdx.x == 0 && r < 100) g_dec_trace[kDecTraceCtas * kDecTraceSlots + 3 * r + 2] = clock64() - t_entry;
       }
       if (gi == ng - 1) {
@@ -517,7 +477,7 @@ static bool dec_carve_with(const DecPlan &plan, int M, int rot_bytes, int sets, 
   const int xb_bytes = plan.ng_max * kDecN * 256;
   const int rot_total = (rot_warps * rot_bytes + 127) / 128 * 128;
   const int recv = plan.c > 1 ? ((plan.nj_max + plan.c - 1) / plan.c) * plan.c * M * 512 : 0;
-  const int bar_bytes = 16 * kDecMaxStages + 256 + (kDecHalves - 1) * 128;
+  const int bar_bytes = 16 * kDecMaxStages + 256;
   const int fixed = xb_bytes + rot_total + recv + bar_bytes + 128;
   int nst = (kDecSmemLimit - fixed) / kDecStage;
   if (nst > kDecMaxStages) nst = kDecMaxStages;
