@@ -1,0 +1,97 @@
+"""Checkpoint I/O: export arithmetic against golden vectors produced by the reference's
+own converter functions (tools/gen_convert_golden.py), on-disk round trip, quantised-module detection, merged projections."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from paroquant_b200 import checkpoint_io as cio
+from paroquant_b200.checkpoint import ParoLayerBuffers, make_synthetic_layer, pack_awq, unpack_awq
+
+GOLD = Path(__file__).parent / "golden" / "ref_convert.npz"
+
+
+def test_export_arithmetic_matches_reference_converter():
+    g = np.load(GOLD)
+    q, s2, z2 = cio.quantize_rotated(torch.from_numpy(g["weight"]), torch.from_numpy(g["scales_flat"]), torch.from_numpy(g["zp_flat"]),
+                                     bits=4, group_size=128)
+    assert np.array_equal(q.numpy(), g["quantized"])                   # integer work: bit-exact
+    assert np.array_equal(z2.numpy(), g["zeros_2d"])
+    assert np.array_equal(s2.numpy(), g["scales_2d"])
+    bufs = cio.to_awq_buffers(q, s2, z2)
+    for k in ("qweight", "qzeros", "scales"):
+        assert np.array_equal(bufs[k].numpy(), g[k]), k
+    assert np.array_equal(pack_awq(torch.from_numpy(g["pack_in"])).numpy(), g["pack_out"])
+    assert np.array_equal(unpack_awq(torch.from_numpy(g["pack_out"])).numpy(), g["pack_in"])
+
+
+def _names(prefix, L: ParoLayerBuffers):
+    t = {f"{prefix}.qweight": L.qweight, f"{prefix}.qzeros": L.qzeros, f"{prefix}.scales": L.scales, f"{prefix}.theta": L.theta[0],
+         f"{prefix}.pairs": L.pairs[0], f"{prefix}.channel_scales": L.channel_scales[0]}
+    if L.bias is not None:
+        t[f"{prefix}.bias"] = L.bias
+    return t
+
+
+def _write_model(tmp_path):
+    q = make_synthetic_layer(256, [256], seed=1, bias=True)
+    k = make_synthetic_layer(256, [128], seed=2, bias=True)
+    v = make_synthetic_layer(256, [128], seed=3, bias=True)
+    o = make_synthetic_layer(256, [256], seed=4)
+    tensors = {}
+    for name, L in (("q_proj", q), ("k_proj", k), ("v_proj", v), ("o_proj", o)):
+        tensors.update(_names(f"model.layers.0.self_attn.{name}", L))
+    tensors["model.embed_tokens.weight"] = torch.randn(32, 256).half()
+    tensors["model.visual.proj.weight"] = torch.randn(16, 256).half()          # an unquantised linear: left alone
+    cio.save_paro_checkpoint(tmp_path, tensors, bits=4, group_size=128, krot=8, base_config={"model_type": "llama"})
+    return {"q": q, "k": k, "v": v, "o": o}
+
+
+def test_round_trip_detection_and_merge(tmp_path):
+    src = _write_model(tmp_path)
+    cfg = json.loads((tmp_path / "config.json").read_text())
+    assert cfg["quantization_config"] == {"quant_method": "paroquant", "bits": 4, "group_size": 128, "krot": 8} and cfg["model_type"] == "llama"
+    assert cio.find_quantized_modules(tmp_path) == {f"model.layers.0.self_attn.{n}" for n in ("q_proj", "k_proj", "v_proj", "o_proj")}
+    ck = cio.load_paro_checkpoint(tmp_path)
+    assert set(ck.dense) == {"model.embed_tokens.weight", "model.visual.proj.weight"}
+    got = ck.layers["model.layers.0.self_attn.k_proj"]
+    for name in ("qweight", "qzeros", "scales", "theta", "pairs", "channel_scales", "bias"):
+        assert torch.equal(getattr(got, name), getattr(src["k"], name)), name
+    assert got.part_sizes == [128] and got.krot == 8 and got.in_features == 256
+
+    merged = cio.merged_view(ck)
+    assert set(merged) == {"model.layers.0.self_attn.qkv_proj", "model.layers.0.self_attn.o_proj"}
+    qkv = merged["model.layers.0.self_attn.qkv_proj"]
+    assert qkv.part_sizes == [256, 128, 128] and qkv.out_features == 512 and qkv.theta.shape == (3, 8, 128)
+    assert torch.equal(unpack_awq(qkv.qweight)[:, 256:384], unpack_awq(src["k"].qweight))   # partitions keep their columns
+    assert torch.equal(qkv.pairs[2], src["v"].pairs[0]) and torch.equal(qkv.bias[384:], src["v"].bias)
+    # the merged layer is exactly what the synthetic generator builds for a fused projection of the same parts
+    assert qkv.numpy_dict()["part_sizes"] == [256, 128, 128]
+
+    ck2 = cio.load_paro_checkpoint(tmp_path, modules_to_not_convert=["model.layers.0.self_attn.o_proj"])
+    assert "model.layers.0.self_attn.o_proj" not in ck2.layers and "model.layers.0.self_attn.o_proj.qweight" in ck2.dense
+
+
+def test_loader_errors(tmp_path):
+    _write_model(tmp_path)
+    (tmp_path / "config.json").write_text(json.dumps({"quantization_config": {"quant_method": "awq"}}))
+    with pytest.raises(ValueError, match="expected 'paroquant'"):
+        cio.load_paro_checkpoint(tmp_path)
+    (tmp_path / "config.json").write_text(json.dumps({"quantization_config": {"quant_method": "paroquant", "bits": 3, "group_size": 128, "krot": 8}}))
+    with pytest.raises(ValueError, match="INT4 group-128 only"):
+        cio.load_paro_checkpoint(tmp_path)
+    (tmp_path / "config.json").write_text(json.dumps({"quantization_config": {"quant_method": "paroquant", "bits": 4, "group_size": 128, "krot": 4}}))
+    with pytest.raises(ValueError, match="buffer shapes do not match"):
+        cio.load_paro_checkpoint(tmp_path)
+    a, b = make_synthetic_layer(256, [128], seed=5, bias=True), make_synthetic_layer(256, [128], seed=6)
+    with pytest.raises(ValueError, match="bias"):
+        cio.merge_layers([a, b])
+    with pytest.raises(ValueError, match="disagree"):
+        cio.merge_layers([a, make_synthetic_layer(384, [128], seed=7, bias=True)])
+
+
+def test_export_layer_is_cuda_only():
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        cio.export_layer({"weight": torch.zeros(8, 128)}, device="cpu")
