@@ -95,3 +95,44 @@ def test_loader_errors(tmp_path):
 def test_export_layer_is_cuda_only():
     with pytest.raises(RuntimeError, match="CUDA-only"):
         cio.export_layer({"weight": torch.zeros(8, 128)}, device="cpu")
+
+
+def test_hf_quantizer_glue_replaces_and_loads(tmp_path):
+    """transformers loader glue (reference quantizer.py:30-115) on a tiny random Llama: only modules with `.qweight`
+    in the checkpoint become RotateQuantizedLinear; the checkpoint then loads into the model strictly."""
+    transformers = pytest.importorskip("transformers")
+    from safetensors.torch import load_file
+    from paroquant_b200.inference.backends.transformers import RotateQuantizedLinear
+    from paroquant_b200.inference.backends.transformers import quantizer as hfq
+
+    cfg = transformers.LlamaConfig(hidden_size=256, intermediate_size=384, num_hidden_layers=1, num_attention_heads=4,
+                                   num_key_value_heads=2, vocab_size=64, tie_word_embeddings=False)
+    model = transformers.LlamaForCausalLM(cfg)
+    tensors = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    quantised = {}
+    for name, mod in model.named_modules():
+        if isinstance(mod, torch.nn.Linear) and ".layers." in name and not name.endswith("down_proj"):   # down_proj stays dense
+            L = make_synthetic_layer(mod.in_features, [mod.out_features], seed=len(quantised) + 11)
+            tensors.pop(f"{name}.weight")
+            tensors.update(_names(name, L))
+            quantised[name] = L
+    cio.save_paro_checkpoint(tmp_path, tensors, krot=8, base_config=cfg.to_dict())
+
+    assert "paroquant" in transformers.quantizers.auto.AUTO_QUANTIZER_MAPPING
+    qz = hfq.ParoQuantHfQuantizer(hfq.ParoQuantConfig(bits=4, group_size=128, krot=8))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="requires CUDA"):
+            qz.validate_environment()
+    assert qz.update_dtype(torch.float32) == torch.float16 and qz.update_dtype(torch.bfloat16) == torch.bfloat16
+    model.config._name_or_path = str(tmp_path)
+    qz._process_model_before_weight_loading(model)
+    swapped = {n for n, m in model.named_modules() if isinstance(m, RotateQuantizedLinear)}
+    assert swapped == set(quantised)
+    assert isinstance(model.get_submodule("model.layers.0.mlp.down_proj"), torch.nn.Linear)
+    assert isinstance(model.lm_head, torch.nn.Linear)
+    missing, unexpected = model.load_state_dict(load_file(str(tmp_path / "model.safetensors")), strict=True)
+    assert not missing and not unexpected
+    name = "model.layers.0.self_attn.k_proj"
+    got = model.get_submodule(name)
+    assert torch.equal(got.qweight, quantised[name].qweight) and torch.equal(got.pairs, quantised[name].pairs[0])
+    assert torch.equal(got.channel_scales, quantised[name].channel_scales[0])
