@@ -143,3 +143,17 @@ def test_vllm_entry_point_is_idempotent(vllm_plugin):
     register()
     register()
     assert hasattr(torch.ops.rotation, "rotate") and hasattr(torch.ops.paro, "linear")
+
+
+def test_shared_workspace_grows_without_invalidating_old_buffers():
+    """All linears of a device share one scratch buffer (pure scratch since the small-M kernel reduces through DSMEM);
+    growing it must keep the previous buffer alive -- CUDA graphs captured earlier hold its pointer."""
+    import torch
+    from paroquant_b200 import linear
+    dev = torch.device("cpu")
+    linear._shared_scratch.pop(dev, None)
+    a = linear.shared_workspace(dev, 10)
+    assert a.numel() == 256 and linear.shared_workspace(dev, 200) is a
+    b = linear.shared_workspace(dev, 4096)
+    assert b.numel() == 4096 and b is not a and linear.shared_workspace(dev, 300) is b
+    assert any(t is a for t in linear._shared_scratch[dev])          # still referenced
