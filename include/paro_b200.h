@@ -126,6 +126,13 @@ int paro_unpack_dense(const paro_linear_shape *shape, const void *packed, void *
  * thread launched (bench.py's gpu_launches accounting).                                  */
 int paro_last_launch_count(void);
 
+/* Test hook (host only, no device work): the launch plan of the M <= 16 kernel for a device with `sms` SMs that keeps
+ * resident_clusters[log2 c] clusters of c = 1, 2, 4, 8 CTAs resident.  out[0..10] = cluster size, block ranges, grid,
+ * max blocks per CTA, max groups per CTA, ring stages, rotating warps, shared-memory bytes, B-operand / receive /
+ * barrier offsets; out[11..19] = first block range of every partition (+ end).                                    */
+int paro_debug_decode_plan(const paro_linear_shape *shape, int64_t M, int32_t sets, int32_t sms,
+                           const int32_t *resident_clusters, int32_t *out);
+
 /* Developer aid: with PARO_DECODE_TRACE=1 in the environment the small-M kernel records, per CTA,
  * 12 uint64 values (phase timestamps in SM cycles relative to kernel entry, %globaltimer at entry
  * and exit).  Copies the first max_ctas x 12 values of the last launch to host_out (synchronous). */

@@ -32,6 +32,7 @@ bool decode_supported(const Layout &L, int64_t M);
 int decode_forward(const paro_linear_shape &s, const Layout &L, const void *packed, const void *x, int64_t M,
                    const void *bias, void *y, cudaStream_t stream);
 int decode_trace_read(unsigned long long *host, int max_ctas);
+int decode_debug_plan(const Layout &L, int64_t M, int sets, int sms, const int32_t *resident4, int32_t *out20);
 size_t gemm_workspace_bytes(const Layout &L, int64_t max_m);
 int gemm_forward(const paro_linear_shape &s, const Layout &L, const void *packed, const void *x, int64_t M,
                  const void *bias, void *y, void *workspace, size_t workspace_bytes, cudaStream_t stream);
@@ -123,6 +124,15 @@ int paro_unpack_dense(const paro_linear_shape *shape, const void *packed, void *
   if (!shape || !make_layout(*shape, L, &why)) { set_error("unpack_dense: %s", shape ? why : "null shape"); return PARO_EINVAL; }
   if (!packed || !W_out) { set_error("unpack_dense: null pointer argument"); return PARO_EINVAL; }
   return unpack_dense_launch(*shape, L, packed, W_out, static_cast<cudaStream_t>(stream));
+}
+
+int paro_debug_decode_plan(const paro_linear_shape *shape, int64_t M, int32_t sets, int32_t sms, const int32_t *resident_clusters,
+                            int32_t *out) {
+  Layout L;
+  const char *why = "";
+  if (!shape || !make_layout(*shape, L, &why)) { set_error("debug_decode_plan: %s", shape ? why : "null shape"); return PARO_EINVAL; }
+  if (!resident_clusters || !out || sms < 1) { set_error("debug_decode_plan: bad arguments"); return PARO_EINVAL; }
+  return decode_debug_plan(L, M, sets, sms, resident_clusters, out);
 }
 
 int paro_debug_trace(unsigned long long *host_out, int32_t max_ctas) {

@@ -534,13 +534,12 @@ static int max_resident_clusters(int c, int smem_bytes, int sms) {
   return n;
 }
 
-template <typename T, int SETS>
-static int launch_decode(DecParams &p, const Layout &L, int sms, cudaStream_t stream) {
-  auto kern = decode_kernel<T, SETS>;
-  const bool cluster_ok = !dec_env_int("PARO_NO_CLUSTER", 0);
-  const int force_c = dec_env_int("PARO_DECODE_C", 0);
-  DecPlan best = {};
-  DecSmem best_s = {};
+// The launch plan: cluster size c (K slices), block ranges per partition, shared-memory carve-up.  Pure host logic --
+// `resident(c, smem_bytes)` says how many clusters of c CTAs with that footprint the device keeps resident (all clusters
+// must be co-resident: one wave) -- so tests can drive it without a GPU (paro_debug_decode_plan).
+template <typename ResidentFn>
+static bool dec_choose_plan(const Layout &L, int M, int rot_bytes, int sets, int sms, bool cluster_ok, int force_c, ResidentFn resident,
+                            DecPlan &best, DecSmem &best_s) {
   long best_cost = -1;
   for (int cs = 0; cs <= 3; ++cs) {
     const int c = 1 << cs;
@@ -552,20 +551,49 @@ static int launch_decode(DecParams &p, const Layout &L, int sms, cudaStream_t st
     plan.ng_max = (L.groups + c - 1) / c;
     if (!dec_split_ranges(L, sms / c, plan)) continue;
     DecSmem s;
-    if (!dec_carve(plan, p.M, p.rot_bytes, SETS, s)) continue;
-    // all clusters must be co-resident (one wave): the device may hold fewer clusters than sms / c
-    const int resident = max_resident_clusters<T, SETS>(c, s.total, sms);
-    if (resident < L.n_parts) continue;
-    if (resident < plan.ranges) {
-      if (!dec_split_ranges(L, resident, plan)) continue;
-      if (!dec_carve(plan, p.M, p.rot_bytes, SETS, s)) continue;
+    if (!dec_carve(plan, M, rot_bytes, sets, s)) continue;
+    const int res = resident(c, s.total);
+    if (res < L.n_parts) continue;
+    if (res < plan.ranges) {
+      if (!dec_split_ranges(L, res, plan)) continue;
+      if (!dec_carve(plan, M, rot_bytes, sets, s)) continue;
     }
     plan.grid = plan.ranges * c;
     // critical path in rounds: main loop of the busiest CTA + rotation passes + a small charge per doubling of the cluster
-    const int passes = (plan.ng_max * (p.M > 4 ? (p.M + 3) / 4 : 1) + 4 * SETS - 1) / (4 * SETS);
-    const long cost = static_cast<long>(plan.nj_max) * plan.ng_max * 8 + passes * 24 + cs * 2;
+    const int passes = (plan.ng_max * (M > 4 ? (M + 3) / 4 : 1) + 4 * sets - 1) / (4 * sets);
+    long cost = static_cast<long>(plan.nj_max) * plan.ng_max * 8 + passes * 24 + cs * 2;
+    if (s.nstages < 2 * sets) cost += cost / 4;   // a ring shallower than two rounds per set starves the dequant warps (large M: the receive buffer crowds it out)
     if (best_cost < 0 || cost < best_cost) { best = plan; best_s = s; best_cost = cost; }
   }
+  return best_cost >= 0;
+}
+
+static int dec_rot_bytes(int64_t M) { return kGroup * 2 * (M == 1 ? 1 : M == 2 ? 2 : 4); }   // rotation tile of one task: 128 channels x up to 4 rows
+
+// test hook: the plan for given resident-cluster counts (index log2 c), no device involved
+int decode_debug_plan(const Layout &L, int64_t M, int sets, int sms, const int32_t *resident4, int32_t *out20) {
+  if (M < 1 || M > 16 || sets < 4 || sets > 7) { set_error("debug_plan: bad M / sets"); return PARO_EINVAL; }
+  DecPlan plan = {};
+  DecSmem sm = {};
+  auto res = [&](int c, int) { int i = 0; while ((1 << i) < c) ++i; return static_cast<int>(resident4[i]); };
+  if (!dec_choose_plan(L, static_cast<int>(M), dec_rot_bytes(M), sets, sms, true, 0, res, plan, sm)) {
+    set_error("decode: no launch configuration fits (in_features=%d, M=%d)", L.K, static_cast<int>(M));
+    return PARO_EUNSUPPORTED;
+  }
+  const int32_t v[11] = {plan.c, plan.ranges, plan.grid, plan.nj_max, plan.ng_max, sm.nstages, sm.rot_warps, sm.total, sm.xb_off, sm.recv_off, sm.bar_off};
+  for (int i = 0; i < 11; ++i) out20[i] = v[i];
+  for (int i = 0; i <= PARO_MAX_PARTS; ++i) out20[11 + i] = plan.part_range_begin[i];
+  return PARO_OK;
+}
+
+template <typename T, int SETS>
+static int launch_decode(DecParams &p, const Layout &L, int sms, cudaStream_t stream) {
+  auto kern = decode_kernel<T, SETS>;
+  DecPlan best = {};
+  DecSmem best_s = {};
+  const bool found = dec_choose_plan(L, p.M, p.rot_bytes, SETS, sms, !dec_env_int("PARO_NO_CLUSTER", 0), dec_env_int("PARO_DECODE_C", 0),
+                                     [&](int c, int smem) { return max_resident_clusters<T, SETS>(c, smem, sms); }, best, best_s);
+  const long best_cost = found ? 0 : -1;
   if (best_cost < 0) { set_error("decode: no launch configuration fits (in_features=%d, M=%d)", L.K, p.M); return PARO_EUNSUPPORTED; }
   if (dec_env_int("PARO_DECODE_VERBOSE", 0))
     fprintf(stderr, "[paro decode] K=%d N=%d M=%d: cluster %d x %d ranges (grid %d), blocks/CTA <= %d, groups/CTA <= %d, %d stages, smem %d\n",
@@ -615,7 +643,7 @@ int decode_forward(const paro_linear_shape &s, const Layout &L, const void *pack
   p.x = x; p.y = y; p.bias = bias;
   p.M = static_cast<int>(M); p.K = L.K; p.N = L.N;
   p.n_parts = L.n_parts; p.groups = L.groups; p.krot = L.krot;
-  p.rot_bytes = kGroup * 2 * (M == 1 ? 1 : M == 2 ? 2 : 4);   // rotation tile of one task: 128 channels x up to 4 rows
+  p.rot_bytes = dec_rot_bytes(M);
   p.trace = dec_env_int("PARO_DECODE_TRACE", 0);
   for (int i = 0; i <= PARO_MAX_PARTS; ++i) {
     p.part_col_begin[i] = L.part_col_begin[i];
