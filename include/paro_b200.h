@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PARO_ABI_VERSION 1
+#define PARO_ABI_VERSION 2
 #define PARO_MAX_PARTS 8
 
 /* element types (activations, rotation parameters, scales) */
@@ -100,9 +100,9 @@ int paro_prepack(const paro_linear_shape *shape, const int32_t *qweight, const i
                  const void *theta, int32_t theta_dtype, const void *channel_scales,
                  int32_t cs_dtype, void *packed, paro_stream_t stream);
 
-/* Bytes of scratch paro_linear_forward needs for up to max_m rows: the rotated activations
- * of the M > 16 path (n_parts x M x K elements).  The M <= 16 kernel reduces its K slices
- * through distributed shared memory and uses none; at least 256 is returned.            */
+/* Bytes of scratch paro_linear_forward needs for up to max_m rows.  Head: the small-M kernel's block counters
+ * (they must be ZERO when the buffer is first used; every launch leaves them zeroed); behind them pure scratch: the
+ * fp32 partial slots of the M <= 16 kernel or the rotated activations of the M > 16 path (n_parts x M x K elements).  */
 size_t paro_workspace_bytes(const paro_linear_shape *shape, int64_t max_m);
 
 /* y[M, N] = rotate_p(x) . dequant(W)[:, part p] for every partition p (+ bias) in ONE call.
@@ -116,6 +116,42 @@ size_t paro_workspace_bytes(const paro_linear_shape *shape, int64_t max_m);
 int paro_linear_forward(const paro_linear_shape *shape, const void *packed, const void *x,
                         int64_t M, const void *bias, void *y, void *workspace,
                         size_t workspace_bytes, paro_stream_t stream);
+
+/* ---- chains: several linears of one decode step (M <= 16) in ONE launch, element-wise neighbours folded in ----------
+ * The reference runs every quantised linear as its own rotate + GEMM kernels (plugin.py:281-311) and leaves what sits
+ * between them to vLLM: fused_add_rms_norm before qkv / gate_up, silu_and_mul before down, the residual add after o /
+ * down (call sites of ParoQuantLinearMethod.apply).  A chain runs up to PARO_CHAIN_MAX_STEPS such linears back to back
+ * inside one persistent kernel: the weight stream of step i + 1 is prefetched while step i drains, and the neighbours
+ * become the x op / epilogue of the adjacent step.                                                                   */
+#define PARO_CHAIN_MAX_STEPS 6
+#define PARO_XOP_NONE 0      /* x as given                                                                          */
+#define PARO_XOP_SILU_MUL 1  /* x[m, k] = T(silu(g[m, k])) * u[m, k]; input is [M, 2K] = [gate | up]  (silu_and_mul) */
+#define PARO_XOP_RMSNORM 2   /* x = T(T(h * rstd) * w), rstd from the previous step's ADD_RESIDUAL statistics        */
+#define PARO_EPI_STORE 0         /* y = T(acc) (+ bias)                                                             */
+#define PARO_EPI_ADD_RESIDUAL 1  /* h = T(y + residual_in) -> residual_out (fused_add_rms_norm's first half)        */
+
+typedef struct paro_chain_step {
+  const paro_linear_shape *shape;
+  const void *packed;        /* device, from paro_prepack                                                          */
+  const void *bias;          /* device [N] or NULL                                                                 */
+  const void *x;             /* device input, ready at launch; NULL = the previous step's output (y, or
+                              * residual_out after an ADD_RESIDUAL epilogue)                                         */
+  void *y;                   /* device [M, N]; may be NULL with PARO_EPI_ADD_RESIDUAL                               */
+  int32_t x_op;              /* PARO_XOP_*                                                                          */
+  int32_t epilogue;          /* PARO_EPI_*                                                                          */
+  const void *residual_in;   /* ADD_RESIDUAL: device [M, N]                                                         */
+  void *residual_out;        /* ADD_RESIDUAL: device [M, N], must not alias residual_in                             */
+  const void *norm_weight;   /* RMSNORM: device [K] of shape->dtype                                                 */
+  float eps;                 /* RMSNORM                                                                             */
+} paro_chain_step;
+
+/* Workspace bytes for paro_chain_forward (0 on an invalid chain).  The workspace must be zero-filled once when it is
+ * allocated; every launch leaves its counters zeroed again.                                                        */
+size_t paro_chain_workspace_bytes(const paro_chain_step *steps, int32_t n_steps, int64_t M);
+
+/* Run the chain for M <= 16 rows.  One launch; CUDA-graph safe; no allocation, no host synchronisation.             */
+int paro_chain_forward(const paro_chain_step *steps, int32_t n_steps, int64_t M, void *workspace,
+                       size_t workspace_bytes, paro_stream_t stream);
 
 /* Debug / test aid: dequantise the prepacked weights back to a dense [K, N] matrix of
  * shape->dtype (the exact operand the GEMM consumes).                                    */
@@ -132,6 +168,15 @@ int paro_last_launch_count(void);
  * barrier offsets; out[11..19] = first block range of every partition (+ end).                                    */
 int paro_debug_decode_plan(const paro_linear_shape *shape, int64_t M, int32_t sets, int32_t sms,
                            const int32_t *resident_clusters, int32_t *out);
+
+/* Test hook (host only): the plan of one step of the small-M kernel on `ctas` CTAs.  out[0..4] = K slices, members per
+ * slice, max contributor slots per block, max groups per CTA, max rounds per CTA; out[5..13] = first member of every
+ * partition's team (+ end).                                                                                          */
+int paro_debug_stream_plan(const paro_linear_shape *shape, int64_t M, int32_t sets, int32_t ctas, int32_t *out);
+
+/* Developer aid: with PARO_DECODE_TRACE=1 the small-M kernel records, per CTA and step, 8 timestamps (SM cycles since
+ * kernel entry).  Copies the first max_ctas x PARO_CHAIN_MAX_STEPS x 8 values of the last launch to host_out.        */
+int paro_debug_stream_trace(unsigned long long *host_out, int32_t max_ctas);
 
 /* Developer aid: with PARO_DECODE_TRACE=1 in the environment the small-M kernel records, per CTA,
  * 12 uint64 values (phase timestamps in SM cycles relative to kernel entry, %globaltimer at entry

@@ -304,6 +304,34 @@ def linear(x_f32, layer: dict, dtype: str = "bfloat16", impl: str = "c", W_cache
     return y
 
 
+# ------------------------------------------------------------------ element-wise neighbours of the linear (chains)
+# The reference leaves these to vLLM (call sites of ParoQuantLinearMethod.apply, plugin.py:281-311): they are restated
+# from vLLM 0.22's kernels -- csrc/activation_kernels.cu (silu_and_mul: T(x / (1 + exp(-x))) * y in T) and
+# csrc/layernorm_kernels.cu (fused_add_rms_norm: z = T(x + residual), variance of z in fp32, T(T(z * rstd) * w)).
+
+def silu_and_mul(gate_up_f32, dtype: str = "bfloat16"):
+    """[.., 2K] -> [.., K]: T(T(silu(gate)) * up)."""
+    a = np.asarray(gate_up_f32, np.float32)
+    K = a.shape[-1] // 2
+    g, u = a[..., :K], a[..., K:]
+    with np.errstate(over="ignore"):
+        act = round_to(g / (np.float32(1.0) + np.exp(-g)).astype(np.float32), dtype)
+    return round_to(act * u, dtype)
+
+
+def add_residual(y_f32, residual_f32, dtype: str = "bfloat16"):
+    """h = T(y + residual) -- the new residual stream of fused_add_rms_norm."""
+    return round_to(np.asarray(y_f32, np.float32) + np.asarray(residual_f32, np.float32), dtype)
+
+
+def rms_norm(h_f32, weight_f32, eps: float, dtype: str = "bfloat16"):
+    """T(T(h * rsqrt(mean(h^2) + eps)) * w), statistics in fp32."""
+    h = np.asarray(h_f32, np.float32)
+    var = (h.astype(np.float64) ** 2).mean(axis=-1, keepdims=True)
+    rstd = (1.0 / np.sqrt(var + eps)).astype(np.float32)
+    return round_to(round_to(h * rstd, dtype) * round_to(weight_f32, dtype), dtype)
+
+
 def rel_err(a, b) -> float:
     """Normwise relative error ||a - b|| / ||b|| in float64 (the parity metric)."""
     a = np.asarray(a, np.float64).ravel()

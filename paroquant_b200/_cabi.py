@@ -32,6 +32,22 @@ class ParoLinearShape(ctypes.Structure):
                 tuple(self.part_sizes[: self.n_parts]))
 
 
+class ParoChainStep(ctypes.Structure):
+    """struct paro_chain_step"""
+
+    _fields_ = [
+        ("shape", ctypes.POINTER(ParoLinearShape)), ("packed", ctypes.c_void_p), ("bias", ctypes.c_void_p),
+        ("x", ctypes.c_void_p), ("y", ctypes.c_void_p), ("x_op", ctypes.c_int32), ("epilogue", ctypes.c_int32),
+        ("residual_in", ctypes.c_void_p), ("residual_out", ctypes.c_void_p), ("norm_weight", ctypes.c_void_p),
+        ("eps", ctypes.c_float),
+    ]
+
+
+ABI_VERSION = 2
+CHAIN_MAX_STEPS = 6
+XOP_NONE, XOP_SILU_MUL, XOP_RMSNORM = 0, 1, 2
+EPI_STORE, EPI_ADD_RESIDUAL = 0, 1
+
 _lib = None
 
 
@@ -63,7 +79,15 @@ def lib() -> ctypes.CDLL:
         L.paro_unpack_dense.argtypes = [shp, vp, vp, vp]
         L.paro_debug_trace.restype = ctypes.c_int
         L.paro_debug_trace.argtypes = [vp, i32]
-        if L.paro_abi_version() != 1:
+        L.paro_chain_workspace_bytes.restype = sz
+        L.paro_chain_workspace_bytes.argtypes = [ctypes.POINTER(ParoChainStep), i32, i64]
+        L.paro_chain_forward.restype = ctypes.c_int
+        L.paro_chain_forward.argtypes = [ctypes.POINTER(ParoChainStep), i32, i64, vp, sz, vp]
+        L.paro_debug_stream_plan.restype = ctypes.c_int
+        L.paro_debug_stream_plan.argtypes = [shp, i64, i32, i32, ctypes.POINTER(ctypes.c_int32)]
+        L.paro_debug_stream_trace.restype = ctypes.c_int
+        L.paro_debug_stream_trace.argtypes = [vp, i32]
+        if L.paro_abi_version() != ABI_VERSION:
             raise ImportError("libparo_b200.so ABI version mismatch")
         _lib = L
     return _lib
@@ -72,6 +96,7 @@ def lib() -> ctypes.CDLL:
 EXPORTED_SYMBOLS = (
     "paro_abi_version", "paro_last_error", "paro_last_launch_count", "paro_rotate", "paro_packed_bytes",
     "paro_prepack", "paro_workspace_bytes", "paro_linear_forward", "paro_unpack_dense", "paro_debug_trace", "paro_debug_decode_plan",
+    "paro_chain_workspace_bytes", "paro_chain_forward", "paro_debug_stream_plan", "paro_debug_stream_trace",
 )
 
 
@@ -193,8 +218,8 @@ def linear_forward(shape: ParoLinearShape, packed: torch.Tensor, x: torch.Tensor
     M = x.numel() // shape.in_features
     if out is None:
         out = torch.empty(*x.shape[:-1], shape.out_features, dtype=x.dtype, device=dev)
-    if bias is not None:
-        bias = bias.to(x.dtype).contiguous()
+    if bias is not None and (bias.dtype != x.dtype or not bias.is_contiguous()):
+        raise RuntimeError(f"linear_forward: bias must be a contiguous {x.dtype} tensor (ParoLinearKernel casts it once)")
     if M == 0:
         return out
     need = workspace_bytes(shape, M)
@@ -219,3 +244,18 @@ def unpack_dense(shape: ParoLinearShape, packed: torch.Tensor) -> torch.Tensor:
 
 def last_launch_count() -> int:
     return lib().paro_last_launch_count()
+
+
+def chain_workspace_bytes(steps, n: int, M: int) -> int:
+    nb = lib().paro_chain_workspace_bytes(steps, n, M)
+    if nb == 0:
+        raise RuntimeError(f"chain: {lib().paro_last_error().decode()}")
+    return nb
+
+
+def chain_forward(steps, n: int, M: int, workspace: torch.Tensor) -> None:
+    """paro_chain_forward on the current stream of the workspace's device (steps: ctypes array of ParoChainStep)."""
+    dev = workspace.device
+    with torch.cuda.device(dev):
+        rc = lib().paro_chain_forward(steps, n, M, workspace.data_ptr(), workspace.numel(), _stream(dev))
+    _check(rc, "chain_forward")

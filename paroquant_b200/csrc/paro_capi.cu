@@ -7,6 +7,7 @@
 
 #include "paro_common.cuh"
 #include "paro_layout.h"
+#include "paro_stream.h"
 
 namespace paro {
 
@@ -33,6 +34,15 @@ int decode_forward(const paro_linear_shape &s, const Layout &L, const void *pack
                    const void *bias, void *y, cudaStream_t stream);
 int decode_trace_read(unsigned long long *host, int max_ctas);
 int decode_debug_plan(const Layout &L, int64_t M, int sets, int sms, const int32_t *resident4, int32_t *out20);
+bool stream_supported(const Layout &L, int64_t M);
+size_t stream_sync_bytes(const Layout &L);
+size_t stream_workspace_bytes(const Layout &L, int64_t max_m);
+size_t stream_chain_workspace_bytes(const HostStep *steps, int n, int64_t M);
+int stream_forward(const HostStep *steps, int n, int64_t M, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+int stream_linear_forward(const paro_linear_shape &s, const Layout &L, const void *packed, const void *x, int64_t M, const void *bias, void *y,
+                          void *workspace, size_t workspace_bytes, cudaStream_t stream);
+int stream_trace_read(unsigned long long *host, int max_ctas);
+int stream_debug_plan(const Layout &L, int64_t M, int sets, int ctas, int32_t *out);
 size_t gemm_workspace_bytes(const Layout &L, int64_t max_m);
 int gemm_forward(const paro_linear_shape &s, const Layout &L, const void *packed, const void *x, int64_t M,
                  const void *bias, void *y, void *workspace, size_t workspace_bytes, cudaStream_t stream);
@@ -94,8 +104,13 @@ size_t paro_workspace_bytes(const paro_linear_shape *shape, int64_t max_m) {
   Layout L;
   const char *why = "";
   if (!shape || !make_layout(*shape, L, &why)) { set_error("workspace_bytes: %s", shape ? why : "null shape"); return 0; }
-  // the small-M kernel reduces through distributed shared memory and needs no global scratch; M > 16 stages x_rot
-  const size_t b = max_m > 16 ? gemm_workspace_bytes(L, max_m) : 0;
+  // head: sync words + block counters of the small-M kernel (zero between calls); behind them scratch: the partial slots
+  // of the small-M kernel or the rotated activations of the M > 16 path
+  size_t b = stream_workspace_bytes(L, max_m);
+  if (max_m > 16) {
+    const size_t g = stream_sync_bytes(L) + gemm_workspace_bytes(L, max_m);
+    if (g > b) b = g;
+  }
   return b > 256 ? b : 256;
 }
 
@@ -113,8 +128,14 @@ int paro_linear_forward(const paro_linear_shape *shape, const void *packed, cons
     return PARO_EINVAL;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (M <= 16) return decode_forward(*shape, L, packed, x, M, bias, y, st);   // one persistent CTA per SM (paro_decode.cu)
-  return gemm_forward(*shape, L, packed, x, M, bias, y, workspace, workspace_bytes, st);
+  if (M <= 16) {   // one persistent CTA per SM (paro_stream.cu)
+    static const bool v1 = [] { const char *v = getenv("PARO_DECODE_V1"); return v && *v && atoi(v) != 0; }();
+    if (v1) return decode_forward(*shape, L, packed, x, M, bias, y, st);
+    return stream_linear_forward(*shape, L, packed, x, M, bias, y, workspace, workspace_bytes, st);
+  }
+  const size_t head = stream_sync_bytes(L);   // never touched by the large-M path
+  if (workspace_bytes < head) { set_error("workspace too small: have %zu, need %zu", workspace_bytes, head); return PARO_EWORKSPACE; }
+  return gemm_forward(*shape, L, packed, x, M, bias, y, static_cast<uint8_t *>(workspace) + head, workspace_bytes - head, st);
 }
 
 int paro_unpack_dense(const paro_linear_shape *shape, const void *packed, void *W_out, paro_stream_t stream) {
@@ -133,6 +154,63 @@ int paro_debug_decode_plan(const paro_linear_shape *shape, int64_t M, int32_t se
   if (!shape || !make_layout(*shape, L, &why)) { set_error("debug_decode_plan: %s", shape ? why : "null shape"); return PARO_EINVAL; }
   if (!resident_clusters || !out || sms < 1) { set_error("debug_decode_plan: bad arguments"); return PARO_EINVAL; }
   return decode_debug_plan(L, M, sets, sms, resident_clusters, out);
+}
+
+static int chain_to_host(const paro_chain_step *steps, int32_t n, int64_t M, HostStep *hs) {
+  if (!steps || n < 1 || n > PARO_CHAIN_MAX_STEPS) { set_error("chain: 1..%d steps supported", PARO_CHAIN_MAX_STEPS); return PARO_EINVAL; }
+  if (M < 1 || M > 16) { set_error("chain: 1 <= M <= 16 rows supported, got %lld", static_cast<long long>(M)); return PARO_EUNSUPPORTED; }
+  for (int i = 0; i < n; ++i) {
+    const paro_chain_step &c = steps[i];
+    const char *why = "";
+    if (!c.shape || !make_layout(*c.shape, hs[i].L, &why)) { set_error("chain: step %d: %s", i, c.shape ? why : "null shape"); return PARO_EINVAL; }
+    if (!c.packed) { set_error("chain: step %d: null packed buffer", i); return PARO_EINVAL; }
+    if (c.x_op < PARO_XOP_NONE || c.x_op > PARO_XOP_RMSNORM || c.epilogue < PARO_EPI_STORE || c.epilogue > PARO_EPI_ADD_RESIDUAL) {
+      set_error("chain: step %d: unknown x_op / epilogue", i);
+      return PARO_EINVAL;
+    }
+    if (!aligned(c.packed, 128) || !aligned(c.x, 16) || !aligned(c.y, 16) || !aligned(c.residual_in, 16) || !aligned(c.residual_out, 16)) {
+      set_error("chain: step %d: packed must be 128-byte, activations 16-byte aligned", i);
+      return PARO_EINVAL;
+    }
+    if (c.epilogue == PARO_EPI_ADD_RESIDUAL && c.residual_in == c.residual_out && c.residual_in) {
+      set_error("chain: step %d: residual_out must not alias residual_in", i);
+      return PARO_EINVAL;
+    }
+    hs[i].shape = c.shape;
+    hs[i].packed = c.packed; hs[i].bias = c.bias; hs[i].x = c.x; hs[i].y = c.y;
+    hs[i].x_op = c.x_op; hs[i].epi_op = c.epilogue;
+    hs[i].res_in = c.residual_in; hs[i].res_out = c.residual_out; hs[i].norm_w = c.norm_weight; hs[i].eps = c.eps;
+  }
+  return PARO_OK;
+}
+
+size_t paro_chain_workspace_bytes(const paro_chain_step *steps, int32_t n_steps, int64_t M) {
+  HostStep hs[PARO_CHAIN_MAX_STEPS] = {};
+  if (chain_to_host(steps, n_steps, M, hs) != PARO_OK) return 0;
+  return stream_chain_workspace_bytes(hs, n_steps, M);
+}
+
+int paro_chain_forward(const paro_chain_step *steps, int32_t n_steps, int64_t M, void *workspace, size_t workspace_bytes,
+                       paro_stream_t stream) {
+  g_launches = 0;
+  HostStep hs[PARO_CHAIN_MAX_STEPS] = {};
+  const int rc = chain_to_host(steps, n_steps, M, hs);
+  if (rc != PARO_OK) return rc;
+  if (!workspace || !aligned(workspace, 256)) { set_error("chain: workspace must be a 256-byte aligned device buffer"); return PARO_EINVAL; }
+  return stream_forward(hs, n_steps, M, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int paro_debug_stream_plan(const paro_linear_shape *shape, int64_t M, int32_t sets, int32_t ctas, int32_t *out) {
+  Layout L;
+  const char *why = "";
+  if (!shape || !make_layout(*shape, L, &why)) { set_error("debug_stream_plan: %s", shape ? why : "null shape"); return PARO_EINVAL; }
+  if (!out) { set_error("debug_stream_plan: bad arguments"); return PARO_EINVAL; }
+  return stream_debug_plan(L, M, sets, ctas, out);
+}
+
+int paro_debug_stream_trace(unsigned long long *host_out, int32_t max_ctas) {
+  if (!host_out || max_ctas <= 0) { set_error("debug_trace: bad arguments"); return PARO_EINVAL; }
+  return stream_trace_read(host_out, max_ctas);
 }
 
 int paro_debug_trace(unsigned long long *host_out, int32_t max_ctas) {

@@ -14,7 +14,7 @@ from . import _cabi
 from .checkpoint import ParoLayerBuffers, validate_pairs
 
 torch.library.define(
-    "paro::linear", "(Tensor x, Tensor packed, Tensor(a!) workspace, Tensor? bias, int[] meta) -> Tensor")
+    "paro::linear", "(Tensor x, Tensor packed, Tensor(a!)? workspace, Tensor? bias, int[] meta) -> Tensor")
 
 _shape_cache: dict[tuple, _cabi.ParoLinearShape] = {}
 
@@ -30,7 +30,13 @@ def _shape_from_meta(meta) -> _cabi.ParoLinearShape:
 
 @torch.library.impl("paro::linear", "CUDA")
 def _linear_cuda(x, packed, workspace, bias, meta):
-    return _cabi.linear_forward(_shape_from_meta(meta), packed, x, bias, workspace)
+    # Everything that looks at sizes lives HERE, inside the opaque op: torch.compile / vLLM trace `__call__` with a symbolic
+    # batch dimension and must see a branch-free call (no ctypes, no `m > max_m`).
+    shape = _shape_from_meta(meta)
+    if workspace is None:
+        m = x.numel() // shape.in_features
+        workspace = shared_workspace(x.device, _cabi.workspace_bytes(shape, max(m, 1)))
+    return _cabi.linear_forward(shape, packed, x, bias, workspace)
 
 
 @torch.library.register_fake("paro::linear")
@@ -38,35 +44,48 @@ def _linear_fake(x, packed, workspace, bias, meta):
     return x.new_empty(*x.shape[:-1], sum(int(v) for v in meta[4:]))
 
 
-# paro_linear_forward treats its workspace as pure scratch (the rotated activations of the M > 16 path), and the linears
-# of a model run one after another on a stream: ONE buffer per device serves them all (a private one per layer would be
-# n_parts * M * K * 2 bytes each -- gigabytes for a 32-layer model at 4096 tokens).  Buffers are only ever replaced by
-# larger ones and the old ones stay alive, so CUDA graphs captured earlier keep valid pointers.
+# paro_linear_forward's workspace is scratch (partial slots of the M <= 16 kernel, rotated activations of the M > 16 path)
+# behind a 256-byte head that holds the launch epoch, and the linears of a model run one after another on a stream: ONE
+# buffer per device serves them all (a private one per layer would be n_parts * M * K * 2 bytes each -- gigabytes for a
+# 32-layer model at 4096 tokens).  It grows geometrically (at least 2x), so a workload whose batch creeps up allocates
+# O(log) buffers; superseded buffers stay alive because CUDA graphs captured earlier hold their addresses, and their sizes
+# sum to less than the current one.  `reserve()` sizes it once up front (vLLM: max_num_batched_tokens).
 _shared_scratch: dict[torch.device, list[torch.Tensor]] = {}
 
 
 def shared_workspace(device, nbytes: int) -> torch.Tensor:
     dev = torch.device(device)
+    if dev.type == "cuda" and dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
     bufs = _shared_scratch.setdefault(dev, [])
     if not bufs or bufs[-1].numel() < nbytes:
-        bufs.append(torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=dev))
+        grow = max(int(nbytes), 2 * bufs[-1].numel() if bufs else 0, 1 << 20)
+        bufs.append(torch.zeros(grow, dtype=torch.uint8, device=dev))
     return bufs[-1]
+
+
+def reserve(device, shapes, max_tokens: int) -> None:
+    """Size the shared scratch once for every linear shape of a model at `max_tokens` rows."""
+    need = max(_cabi.workspace_bytes(s, max_tokens) for s in shapes)
+    shared_workspace(device, need)
 
 
 class ParoLinearKernel:
     """Prepacked weights + rotation metadata of one (possibly merged) linear on one GPU.
-    `private_workspace=True` gives the layer its own scratch (needed only when two linears may run concurrently on
-    different streams; include/paro_b200.h: a workspace must not be shared by concurrent launches)."""
+    `private_workspace=True` gives the layer its own scratch sized for `max_m` rows (needed only when two linears may run
+    concurrently on different streams; include/paro_b200.h: a workspace must not be shared by concurrent launches);
+    otherwise the per-device shared scratch is used and sized inside the op."""
 
     def __init__(self, packed: torch.Tensor, shape: _cabi.ParoLinearShape, max_m: int = 16, private_workspace: bool = False):
         self.packed = packed
         self.shape = shape
-        self.meta = [shape.in_features, shape.group_size, shape.krot, shape.dtype,
-                     *list(shape.part_sizes[: shape.n_parts])]
+        self.meta = [int(shape.in_features), int(shape.group_size), int(shape.krot), int(shape.dtype),
+                     *[int(v) for v in shape.part_sizes[: shape.n_parts]]]
+        self.dtype = _cabi._CODE_DTYPE[shape.dtype]
         self.private_workspace = private_workspace
-        self.max_m = 0
-        self.workspace = None
-        self._ensure_workspace(max_m)
+        self._private = _cabi.new_workspace(shape, max_m, packed.device) if private_workspace else None
+        self._bias_cache: tuple | None = None
+        shared_workspace(packed.device, _cabi.workspace_bytes(shape, max_m))   # warm the shared scratch outside any capture
 
     @classmethod
     def from_tensors(cls, qweight, qzeros, scales, theta, pairs, channel_scales, part_sizes, *,
@@ -87,19 +106,28 @@ class ParoLinearKernel:
         return cls.from_tensors(b.qweight, b.qzeros, b.scales, b.theta, b.pairs, b.channel_scales, b.part_sizes,
                                 group_size=b.group_size, dtype=dtype, **kw)
 
-    def _ensure_workspace(self, m: int) -> None:
-        if self.workspace is None or m > self.max_m:
-            if self.private_workspace:
-                self.workspace = _cabi.new_workspace(self.shape, m, self.packed.device)
-            else:
-                self.workspace = shared_workspace(self.packed.device, _cabi.workspace_bytes(self.shape, m))
-            self.max_m = m
+    @property
+    def workspace(self) -> torch.Tensor:
+        """The scratch the next launch will use (tools and benches that call the C-ABI directly)."""
+        return self._private if self._private is not None else shared_workspace(self.packed.device, 0)
+
+    def _bias(self, bias: torch.Tensor | None) -> torch.Tensor | None:
+        """Bias in the activation dtype; a checkpoint's fp16 bias meeting bf16 activations is cast ONCE, not per forward."""
+        if bias is None or (bias.dtype == self.dtype and bias.is_contiguous()):
+            return bias
+        c = self._bias_cache
+        if c is None or c[0] is not bias or c[1] != bias._version:
+            self._bias_cache = c = (bias, bias._version, bias.to(self.dtype).contiguous())
+        return c[2]
 
     def __call__(self, x: torch.Tensor, bias: torch.Tensor | None = None) -> torch.Tensor:
+        return torch.ops.paro.linear(x, self.packed, self._private, self._bias(bias), self.meta)
+
+    def forward_into(self, x: torch.Tensor, out: torch.Tensor, bias: torch.Tensor | None = None) -> torch.Tensor:
+        """Same as __call__ but writes into a caller-owned [.., N] buffer (fixed addresses for CUDA graphs / chains)."""
         m = x.numel() // self.shape.in_features
-        if m > self.max_m:
-            self._ensure_workspace(m)
-        return torch.ops.paro.linear(x, self.packed, self.workspace, bias, self.meta)
+        ws = self._private if self._private is not None else shared_workspace(x.device, _cabi.workspace_bytes(self.shape, max(m, 1)))
+        return _cabi.linear_forward(self.shape, self.packed, x, self._bias(bias), ws, out=out)
 
     def dense_weight(self) -> torch.Tensor:
         """[K, N] dequantised operand T((q - z) * s) exactly as the kernels form it (tests)."""

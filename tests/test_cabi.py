@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/paro_b200.h but not exported"
     assert set(names) == set(_cabi.EXPORTED_SYMBOLS)
-    assert lib.paro_abi_version() == 1
+    assert lib.paro_abi_version() == _cabi.ABI_VERSION
 
 
 def test_struct_layout_matches_header():

@@ -8,7 +8,7 @@ as paroquant_b200.kernels.cuda.  Nothing from paroquant_b200's kernels is import
 
     python tools/ref_gpu.py golden  <outdir>          fixtures for tests/golden/
     python tools/ref_gpu.py run     <in.npz> <out.npz> reference outputs for a test's inputs
-    python tools/ref_gpu.py bench   <out.json> [--m 1]  per-linear timings of rotate + Marlin
+    python tools/ref_gpu.py bench   <out.json> [--m 1,16,4096]  per-linear timings of rotate + Marlin (CUDA graph)
 """
 from __future__ import annotations
 
@@ -142,29 +142,56 @@ def run(inp: Path, out: Path) -> None:
     np.savez(out, **res)
 
 
-def bench(out: Path, m: int) -> None:
+def bench(out: Path, ms: list[int]) -> None:
+    """Per-linear time of the reference pair (its rotate kernel per partition -> vLLM AWQ-Marlin per partition -> cat,
+    plugin.py:288-311) on the Llama-3-8B shapes, like-for-like with tools/microbench.py: distinct weight sets > L2,
+    the sweep captured as ONE CUDA graph (no launch overhead), CUDA events around several replays."""
     rotate = load_reference_rotate()
     shapes = {"qkv": (4096, [4096, 1024, 1024]), "o": (4096, [4096]), "gate_up": (4096, [14336, 14336]), "down": (14336, [4096])}
     res = {}
     for name, (K, parts) in shapes.items():
-        # several distinct weight sets so the working set exceeds the 126 MB L2
-        nsets = max(2, int(300e6 // (K * sum(parts) // 2)) + 1)
+        nsets = max(3, int(400e6 // (K * sum(parts) // 2)) + 1)
         layers = [ReferenceLinear(make_synthetic_layer(K, parts, seed=500 + s, device="cuda"), torch.bfloat16, rotate) for s in range(nsets)]
-        x = make_synthetic_activations(m, K, seed=7, device="cuda")
-        for l in layers:
-            l(x)
-        torch.cuda.synchronize()
-        iters = 20
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for it in range(iters):
-            for l in layers:
-                l(x)
-        e1.record()
-        torch.cuda.synchronize()
-        res[name] = {"us_per_linear": e0.elapsed_time(e1) * 1e3 / (iters * nsets), "weight_sets": nsets, "M": m}
+        for m in ms:
+            x = make_synthetic_activations(m, K, seed=7, device="cuda")
+
+            def sweep():
+                for l in layers:
+                    l(x)
+
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                sweep()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            mode = "cuda_graph"
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    sweep()
+                run = g.replay
+            except Exception as e:  # report eager numbers rather than nothing
+                mode = f"eager ({type(e).__name__})"
+                run = sweep
+            for _ in range(3):
+                run()
+            torch.cuda.synchronize()
+            iters = 20 if m <= 256 else 5
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                run()
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / (iters * nsets)
+            res[f"{name}_m{m}"] = {"shape": name, "M": m, "us_per_linear": us, "weight_sets": nsets, "mode": mode,
+                                   "kernels_per_linear": 2 * len(parts) + (1 if len(parts) > 1 else 0),
+                                   "tflops": 2.0 * m * K * sum(parts) / us / 1e6}
+            print(f"{name:8s} M={m:5d} {us:9.2f} us  ({mode})", flush=True)
+        del layers
+        torch.cuda.empty_cache()
     out.write_text(json.dumps(res, indent=1))
-    print(json.dumps(res))
 
 
 if __name__ == "__main__":
@@ -174,4 +201,4 @@ if __name__ == "__main__":
     elif cmd == "run":
         run(Path(sys.argv[2]), Path(sys.argv[3]))
     elif cmd == "bench":
-        bench(Path(sys.argv[2]), int(sys.argv[4]) if len(sys.argv) > 4 else 1)
+        bench(Path(sys.argv[2]), [int(v) for v in sys.argv[4].split(",")] if len(sys.argv) > 4 else [1])
