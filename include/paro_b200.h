@@ -130,6 +130,17 @@ int paro_linear_forward(const paro_linear_shape *shape, const void *packed, cons
 #define PARO_EPI_STORE 0         /* y = T(acc) (+ bias)                                                             */
 #define PARO_EPI_ADD_RESIDUAL 1  /* h = T(y + residual_in) -> residual_out (fused_add_rms_norm's first half)        */
 
+/* Tensor parallelism inside a step (row-sharded K: o_proj / down_proj, reference sharding plugin.py:33-50): every rank's
+ * block sums are written into every rank's `peer_slots` buffer over NVLink and added in rank order by the kernel itself --
+ * the all-reduce vLLM issues after ParoQuantLinearMethod.apply (RowParallelLinear.forward) happens inside the launch.
+ * peer_slots[r] = device address, valid on THIS GPU, of rank r's buffer of paro_tp_slot_bytes() bytes (peer-mapped memory:
+ * CUDA IPC / symmetric memory), zero-filled once.  All ranks must launch the same chains in the same order.            */
+#define PARO_TP_MAX_RANKS 8
+typedef struct paro_tp_info {
+  int32_t world, rank;
+  void *peer_slots[PARO_TP_MAX_RANKS];
+} paro_tp_info;
+
 typedef struct paro_chain_step {
   const paro_linear_shape *shape;
   const void *packed;        /* device, from paro_prepack                                                          */
@@ -143,7 +154,11 @@ typedef struct paro_chain_step {
   void *residual_out;        /* ADD_RESIDUAL: device [M, N], must not alias residual_in                             */
   const void *norm_weight;   /* RMSNORM: device [K] of shape->dtype                                                 */
   float eps;                 /* RMSNORM                                                                             */
+  const paro_tp_info *tp;    /* NULL, or: this step's K is sharded over tp->world ranks, sum the partial outputs      */
 } paro_chain_step;
+
+/* Bytes of the per-rank peer_slots buffer of one tensor-parallel step (0 on an invalid shape).                        */
+size_t paro_tp_slot_bytes(const paro_linear_shape *shape, int64_t M, int32_t world);
 
 /* Workspace bytes for paro_chain_forward (0 on an invalid chain).  The workspace must be zero-filled once when it is
  * allocated; every launch leaves its counters zeroed again.                                                        */

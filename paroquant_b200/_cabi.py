@@ -32,6 +32,12 @@ class ParoLinearShape(ctypes.Structure):
                 tuple(self.part_sizes[: self.n_parts]))
 
 
+class ParoTpInfo(ctypes.Structure):
+    """struct paro_tp_info"""
+
+    _fields_ = [("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("peer_slots", ctypes.c_void_p * 8)]
+
+
 class ParoChainStep(ctypes.Structure):
     """struct paro_chain_step"""
 
@@ -39,7 +45,7 @@ class ParoChainStep(ctypes.Structure):
         ("shape", ctypes.POINTER(ParoLinearShape)), ("packed", ctypes.c_void_p), ("bias", ctypes.c_void_p),
         ("x", ctypes.c_void_p), ("y", ctypes.c_void_p), ("x_op", ctypes.c_int32), ("epilogue", ctypes.c_int32),
         ("residual_in", ctypes.c_void_p), ("residual_out", ctypes.c_void_p), ("norm_weight", ctypes.c_void_p),
-        ("eps", ctypes.c_float),
+        ("eps", ctypes.c_float), ("tp", ctypes.POINTER(ParoTpInfo)),
     ]
 
 
@@ -83,6 +89,8 @@ def lib() -> ctypes.CDLL:
         L.paro_chain_workspace_bytes.argtypes = [ctypes.POINTER(ParoChainStep), i32, i64]
         L.paro_chain_forward.restype = ctypes.c_int
         L.paro_chain_forward.argtypes = [ctypes.POINTER(ParoChainStep), i32, i64, vp, sz, vp]
+        L.paro_tp_slot_bytes.restype = sz
+        L.paro_tp_slot_bytes.argtypes = [shp, i64, i32]
         L.paro_debug_stream_plan.restype = ctypes.c_int
         L.paro_debug_stream_plan.argtypes = [shp, i64, i32, i32, ctypes.POINTER(ctypes.c_int32)]
         L.paro_debug_stream_trace.restype = ctypes.c_int
@@ -96,7 +104,7 @@ def lib() -> ctypes.CDLL:
 EXPORTED_SYMBOLS = (
     "paro_abi_version", "paro_last_error", "paro_last_launch_count", "paro_rotate", "paro_packed_bytes",
     "paro_prepack", "paro_workspace_bytes", "paro_linear_forward", "paro_unpack_dense", "paro_debug_trace", "paro_debug_decode_plan",
-    "paro_chain_workspace_bytes", "paro_chain_forward", "paro_debug_stream_plan", "paro_debug_stream_trace",
+    "paro_chain_workspace_bytes", "paro_chain_forward", "paro_debug_stream_plan", "paro_debug_stream_trace", "paro_tp_slot_bytes",
 )
 
 

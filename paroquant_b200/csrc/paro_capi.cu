@@ -47,6 +47,16 @@ size_t gemm_workspace_bytes(const Layout &L, int64_t max_m);
 int gemm_forward(const paro_linear_shape &s, const Layout &L, const void *packed, const void *x, int64_t M,
                  const void *bias, void *y, void *workspace, size_t workspace_bytes, cudaStream_t stream);
 
+// rows up to which the persistent small-M kernel serves a linear; above, the rotation pre-pass + GEMM path (knob for A/B runs)
+static int small_m_max() {
+  static const int v = [] {
+    const char *e = getenv("PARO_SMALL_M_MAX");
+    const int n = e && *e ? atoi(e) : 16;
+    return n < 0 ? 0 : n > 16 ? 16 : n;
+  }();
+  return v;
+}
+
 static bool valid_dtype(int d) { return d == PARO_F32 || d == PARO_F16 || d == PARO_BF16; }
 static bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
@@ -107,7 +117,7 @@ size_t paro_workspace_bytes(const paro_linear_shape *shape, int64_t max_m) {
   // head: sync words + block counters of the small-M kernel (zero between calls); behind them scratch: the partial slots
   // of the small-M kernel or the rotated activations of the M > 16 path
   size_t b = stream_workspace_bytes(L, max_m);
-  if (max_m > 16) {
+  if (max_m > small_m_max()) {
     const size_t g = stream_sync_bytes(L) + gemm_workspace_bytes(L, max_m);
     if (g > b) b = g;
   }
@@ -128,7 +138,7 @@ int paro_linear_forward(const paro_linear_shape *shape, const void *packed, cons
     return PARO_EINVAL;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (M <= 16) {   // one persistent CTA per SM (paro_stream.cu)
+  if (M <= small_m_max()) {   // one persistent CTA per SM (paro_stream.cu)
     static const bool v1 = [] { const char *v = getenv("PARO_DECODE_V1"); return v && *v && atoi(v) != 0; }();
     if (v1) return decode_forward(*shape, L, packed, x, M, bias, y, st);
     return stream_linear_forward(*shape, L, packed, x, M, bias, y, workspace, workspace_bytes, st);
@@ -180,6 +190,18 @@ static int chain_to_host(const paro_chain_step *steps, int32_t n, int64_t M, Hos
     hs[i].packed = c.packed; hs[i].bias = c.bias; hs[i].x = c.x; hs[i].y = c.y;
     hs[i].x_op = c.x_op; hs[i].epi_op = c.epilogue;
     hs[i].res_in = c.residual_in; hs[i].res_out = c.residual_out; hs[i].norm_w = c.norm_weight; hs[i].eps = c.eps;
+    hs[i].tp = c.tp;
+    if (c.tp) {
+      if (c.tp->world < 1 || c.tp->world > PARO_TP_MAX_RANKS || c.tp->rank < 0 || c.tp->rank >= c.tp->world) {
+        set_error("chain: step %d: tensor-parallel world must be 1..%d and 0 <= rank < world", i, PARO_TP_MAX_RANKS);
+        return PARO_EINVAL;
+      }
+      for (int r = 0; r < c.tp->world; ++r)
+        if (c.tp->world > 1 && (!c.tp->peer_slots[r] || !aligned(c.tp->peer_slots[r], 256))) {
+          set_error("chain: step %d: peer_slots[%d] must be a 256-byte aligned device address", i, r);
+          return PARO_EINVAL;
+        }
+    }
   }
   return PARO_OK;
 }
@@ -198,6 +220,14 @@ int paro_chain_forward(const paro_chain_step *steps, int32_t n_steps, int64_t M,
   if (rc != PARO_OK) return rc;
   if (!workspace || !aligned(workspace, 256)) { set_error("chain: workspace must be a 256-byte aligned device buffer"); return PARO_EINVAL; }
   return stream_forward(hs, n_steps, M, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+size_t paro_tp_slot_bytes(const paro_linear_shape *shape, int64_t M, int32_t world) {
+  Layout L;
+  const char *why = "";
+  if (!shape || !make_layout(*shape, L, &why)) { set_error("tp_slot_bytes: %s", shape ? why : "null shape"); return 0; }
+  if (M < 1 || M > 16 || world < 1 || world > PARO_TP_MAX_RANKS) { set_error("tp_slot_bytes: 1 <= M <= 16, 1 <= world <= %d", PARO_TP_MAX_RANKS); return 0; }
+  return static_cast<size_t>(2) * L.blocks_total * world * M * 128 * 8;
 }
 
 int paro_debug_stream_plan(const paro_linear_shape *shape, int64_t M, int32_t sets, int32_t ctas, int32_t *out) {

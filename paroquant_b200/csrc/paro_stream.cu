@@ -49,6 +49,7 @@ namespace paro {
 
 constexpr int kStmMaxSteps = PARO_CHAIN_MAX_STEPS;
 constexpr int kStmMaxStages = 24;
+constexpr int kStmSets = 5;    // dequant sets of 4 warps (4 and 6 were measured: no better)
 constexpr int kStmABufs = 7;
 constexpr int kStmDBufs = 4;
 constexpr int kStmTmemCols = 512;
@@ -57,7 +58,7 @@ constexpr int kStmN = 16;                        // MMA N (M_mma = 128 needs N %
 constexpr int kStmSmemLimit = 227 * 1024;
 constexpr int kStmStage = kBlockBytes;
 constexpr int kStmBarBytes = 16 * kStmMaxStages + 256;
-constexpr int kStmMiscBytes = 512;               // epilogue scratch: 4 warps x 16 rows of partial sums, the "last" flag
+constexpr int kStmMiscBytes = 4096;              // epilogue scratch: per warp, 64 segments x {block, global block, contributors, my slot | reducer}
 
 constexpr int kStmTraceSlots = 12;
 constexpr int kStmTraceCtas = 160;
@@ -77,10 +78,12 @@ struct StepDesc {
   void *res_out;            // ADD_RESIDUAL: [M, N]  h = T(y + res_in)
   const void *norm_w;       // RMSNORM: [K]
   const uint2 *x_ll;        // x produced by an earlier step of this launch: [M, x_ld] {T bits, tag} words (else null: read x)
-  const uint2 *stats_in;    // RMSNORM: [stats_in_blocks][M] {partial sum of h^2, tag} written by the producing step
-  uint2 *stats_ll;          // ADD_RESIDUAL whose h a later step normalises: [blocks_total][M] {sum of h^2, tag}
+  const uint2 *stats_in;    // RMSNORM: [stats_in_blocks = 4 x blocks][M] {partial sum of h^2, tag} written by the producing step
+  uint2 *stats_ll;          // ADD_RESIDUAL whose h a later step normalises: [blocks_total][4 warps][M] {sum of h^2, tag}
   uint2 *out_ll;            // a later step consumes this step's output: [M, N] {T bits, tag}
   uint2 *slots;             // [blocks_total][max_slots][M][128] {fp32 partial, tag}
+  uint2 *tp_slots[PARO_TP_MAX_RANKS];   // row-parallel step under tensor parallelism: every rank's [2][blocks_total][world][M][128]
+  int tp_world, tp_rank;    // {this rank's block sum, tag} buffer (peer memory over NVLink); tp_world <= 1: none
   float eps;
   int x_op, epi_op;
   int stats_in_blocks;
@@ -98,7 +101,7 @@ struct StreamParams {
   int nstages, nrows_b;       // ring stages; B-operand rows stored per group (8 or 16)
   int rot_bytes, rot_warps;
   int xb_off, rot_off, misc_off, bar_off;
-  int trace;
+  int trace, inflight;        // inflight: bulk copies outstanding per SM
   uint32_t *sync;             // [0] epoch (tag of a launch = epoch + 1), [1] CTAs done
   StepDesc steps[kStmMaxSteps];
 };
@@ -113,25 +116,58 @@ __device__ __forceinline__ StepGeom step_geom(const StepDesc &S, int cta) {
   StepGeom g;
   g.active = 0; g.part = 0; g.slice = 0; g.t = 0; g.Tp = 1; g.g_begin = 0; g.ng = 0; g.blocks_p = 0; g.r0 = 0; g.r1 = 0;
   if (cta >= S.c * S.T) return g;
-  g.slice = cta % S.c;
-  const int u = cta / S.c;
+  const int u = static_cast<int>(static_cast<unsigned>(cta) / static_cast<unsigned>(S.c));
+  g.slice = cta - u * S.c;
   int part = 0;
   while (u >= S.part_cta_begin[part + 1]) ++part;
   g.part = part;
   g.t = u - S.part_cta_begin[part];
   g.Tp = S.part_cta_begin[part + 1] - S.part_cta_begin[part];
-  g.g_begin = g.slice * S.groups / S.c;
-  g.ng = (g.slice + 1) * S.groups / S.c - g.g_begin;
+  g.g_begin = static_cast<int>(static_cast<unsigned>(g.slice * S.groups) / static_cast<unsigned>(S.c));
+  g.ng = static_cast<int>(static_cast<unsigned>((g.slice + 1) * S.groups) / static_cast<unsigned>(S.c)) - g.g_begin;
   g.blocks_p = S.part_block_begin[part + 1] - S.part_block_begin[part];
-  const int Rp = g.blocks_p * g.ng;
-  g.r0 = static_cast<int>(static_cast<long long>(g.t) * Rp / g.Tp);
-  g.r1 = static_cast<int>(static_cast<long long>(g.t + 1) * Rp / g.Tp);
+  // 32-bit on purpose (a 64-bit division is a ~150-instruction subroutine on the GPU): the host checks Rp * Tp < 2^31
+  const unsigned Rp = static_cast<unsigned>(g.blocks_p * g.ng), Tp = static_cast<unsigned>(g.Tp);
+  g.r0 = static_cast<int>(static_cast<unsigned>(g.t) * Rp / Tp);
+  g.r1 = static_cast<int>(static_cast<unsigned>(g.t + 1) * Rp / Tp);
   g.active = g.r1 > g.r0;
   return g;
 }
 // member of a team of Tp over Rp rounds that owns round r (inverse of r0 = t * Rp / Tp)
 __host__ __device__ __forceinline__ int round_owner(int r, int Rp, int Tp) {
-  return static_cast<int>((static_cast<long long>(r + 1) * Tp - 1) / Rp);
+  return static_cast<int>((static_cast<unsigned>(r + 1) * static_cast<unsigned>(Tp) - 1u) / static_cast<unsigned>(Rp));
+}
+
+// The segments of a CTA's run, in the order every role walks them: the run is cut at block boundaries; when it holds whole
+// blocks AND a trailing partial one, the trailing partial block goes right after the leading one -- the blocks shared with
+// the neighbouring team members are then finished early in the step and only whole blocks (which need the other K slices'
+// partials, nothing else) are left for the end.
+struct SegWalk {
+  int r0, r1, ng, a, z, nseg, lead, trail_at;   // a / z: first / last block boundary inside the run
+};
+__device__ __forceinline__ SegWalk seg_walk(const StepGeom &g) {
+  SegWalk w;
+  w.r0 = g.r0; w.r1 = g.r1; w.ng = g.ng;
+  const unsigned ng = static_cast<unsigned>(g.ng);
+  w.a = static_cast<int>((static_cast<unsigned>(g.r0) + ng - 1u) / ng * ng);
+  w.z = static_cast<int>(static_cast<unsigned>(g.r1) / ng * ng);
+  if (w.a >= g.r1) {   // the run lies inside one block
+    w.nseg = 1; w.lead = 1; w.trail_at = -1; w.a = g.r1; w.z = g.r1;
+    return w;
+  }
+  const int nfull = (w.z - w.a) / g.ng;
+  w.lead = g.r0 < w.a ? 1 : 0;
+  const int trail = w.z < g.r1 ? 1 : 0;
+  w.nseg = w.lead + nfull + trail;
+  w.trail_at = trail ? (nfull > 0 ? w.lead : w.nseg - 1) : -1;
+  return w;
+}
+__device__ __forceinline__ void seg_range(const SegWalk &w, int k, int &ra, int &rb) {
+  if (w.trail_at == k) { ra = w.z; rb = w.r1; return; }
+  if (k < w.lead) { ra = w.r0; rb = w.a; return; }
+  const int f = k - w.lead - (w.trail_at >= 0 && k > w.trail_at ? 1 : 0);
+  ra = w.a + f * w.ng;
+  rb = ra + w.ng;
 }
 
 // {value, tag} words: relaxed 8-byte accesses at GPU scope (one access, never torn); the tag validates the value
@@ -152,6 +188,67 @@ __device__ __forceinline__ uint4 ld_relaxed_v4(const uint4 *ptr) {
 }
 __device__ __forceinline__ void st_relaxed_v2(uint2 *ptr, uint32_t a, uint32_t b) {
   asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(ptr), "r"(a), "r"(b) : "memory");
+}
+
+// Adds n sources of {fp32 value, tag} words, source k / row m at src[(k * M + m) * 128], into acc[m] in source order.  A word
+// whose tag is not this launch's is re-read (`wait`) or makes the function give up (returns false).  SYS: the words are
+// written by peer GPUs over NVLink (system scope).
+template <bool SYS> __device__ __forceinline__ uint2 ll_load(const uint2 *ptr) {
+  uint2 v;
+  if constexpr (SYS) asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(ptr) : "memory");
+  else asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(ptr) : "memory");
+  return v;
+}
+template <bool SYS, int MB>
+__device__ __forceinline__ bool ll_sum(const uint2 *src, int n, int M, uint32_t tag, bool wait, float (&acc)[MB]) {
+  bool ready = true;
+  if constexpr (MB == 1) {
+    for (int k0 = 0; k0 < n && ready; k0 += 8) {   // 8 sources in flight
+      uint2 w[8];
+      bool ok;
+      do {
+        ok = true;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          if (k0 + kk < n) {
+            w[kk] = ll_load<SYS>(src + (k0 + kk) * 128);
+            ok = ok && w[kk].y == tag;
+          }
+      } while (!ok && wait);
+      ready = ok;
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk)
+        if (k0 + kk < n) acc[0] += __uint_as_float(w[kk].x);
+    }
+  } else {
+    constexpr int RB = MB < 8 ? MB : 8;   // rows in flight
+    for (int k = 0; k < n && ready; ++k) {   // one source at a time
+#pragma unroll
+      for (int h = 0; h < MB / RB; ++h) {
+        if (RB * h < M && ready) {
+          uint2 w[RB];
+          bool ok;
+          do {
+            ok = true;
+#pragma unroll
+            for (int m = 0; m < RB; ++m)
+              if (RB * h + m < M) {
+                w[m] = ll_load<SYS>(src + (k * M + RB * h + m) * 128);
+                ok = ok && w[m].y == tag;
+              }
+          } while (!ok && wait);
+          ready = ok;
+#pragma unroll
+          for (int m = 0; m < RB; ++m)
+            if (RB * h + m < M) acc[RB * h + m] += __uint_as_float(w[m].x);
+        }
+      }
+    }
+  }
+  return __all_sync(0xFFFFFFFFu, ready);   // a warp handles its 32 columns on its own
+}
+__device__ __forceinline__ void st_relaxed_sys_v2(uint2 *ptr, uint32_t a, uint32_t b) {
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(ptr), "r"(a), "r"(b) : "memory");
 }
 
 // ------------------------------------------------------------------ prologue: x op + rotation + B operand
@@ -245,12 +342,21 @@ __device__ __forceinline__ void stm_load_x(const StepDesc &S, int M, int gk, int
       if (m0 + m < M) {   // warp-uniform
         // sum of the per-block partial sums of h^2 in a fixed order: lane-strided serial sums, then a butterfly
         float s = 0.f;
-        for (int b = lane; b < nb; b += 32) {
-          uint2 e;
+        for (int b0 = lane; b0 < nb; b0 += 128) {   // four words in flight per lane (o / down: 4 x 32 blocks = 128 words)
+          uint2 e[4];
+          bool ok;
           do {
-            e = ld_relaxed_v2(S.stats_in + b * M + m0 + m);
-          } while (e.y != tag);
-          s += __uint_as_float(e.x);
+            ok = true;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (b0 + 32 * u < nb) {
+                e[u] = ld_relaxed_v2(S.stats_in + (b0 + 32 * u) * M + m0 + m);
+                ok = ok && e[u].y == tag;
+              }
+          } while (!ok);
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (b0 + 32 * u < nb) s += __uint_as_float(e[u].x);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
@@ -324,7 +430,8 @@ __device__ __forceinline__ void stm_prologue(const StepDesc &S, int M, int NR, R
 }
 
 // ------------------------------------------------------------------ the kernel
-template <typename T, int SETS>
+// MB: compile-time bound on the rows (M <= MB in {1, 4, 16}) -- sizes the epilogue's per-row registers
+template <typename T, int SETS, int MB>
 __global__ void __launch_bounds__(32 * (4 * SETS + 6), 1) stream_kernel(const __grid_constant__ StreamParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int kWorkers = 4 * SETS;
@@ -334,7 +441,7 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 6), 1) stream_kernel(const __
   const long long t_entry = clock64();
   const int NS = p.nstages, NR = p.nrows_b, M = p.M, nsteps = p.n_steps;
   const uint32_t smem0 = smem_u32(smem);
-  const uint32_t xb = smem0 + p.xb_off, misc = smem0 + p.misc_off, bars = smem0 + p.bar_off;
+  const uint32_t xb = smem0 + p.xb_off, bars = smem0 + p.bar_off;
   const uint32_t bar_wfull = bars, bar_wempty = bars + 8 * kStmMaxStages;
   const uint32_t bar_afull = bars + 16 * kStmMaxStages, bar_afree = bar_afull + 64;
   const uint32_t bar_dfull = bar_afull + 128, bar_dfree = bar_afull + 160;
@@ -377,24 +484,36 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 6), 1) stream_kernel(const __
     // ================= producer: ONE bulk copy per round; nothing here depends on activations, so it runs ahead across
     // step boundaries.  The whole warp runs the loop, an elected lane issues.
     const uint64_t pol = policy_evict_first();
-    int st = 0, it = 0;
+    int st = 0, it = 0, lag_st = 0, lag_it = 0;   // lag_*: stage / wrap of copy number (issued - inflight)
+    uint32_t issued = 0;
 #pragma unroll 1
     for (int i = 0; i < nsteps; ++i) {
       const StepDesc &S = p.steps[i];
       const StepGeom g = step_geom(S, cta);
       if (!g.active) continue;
-      int jb = g.r0 / g.ng, gi = g.r0 - jb * g.ng;
       const uint8_t *rec_part = S.packed + S.rec_off + (static_cast<size_t>(S.part_block_begin[g.part]) * S.groups + g.g_begin) * kBlockBytes;
+      const SegWalk sw = seg_walk(g);
 #pragma unroll 1
-      for (int r = g.r0; r < g.r1; ++r) {
-        if (it > 0) mbar_wait(bar_wempty + 8 * st, (it - 1) & 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(bar_wfull + 8 * st, kBlockBytes);
-          bulk_g2s(smem0 + st * kStmStage, rec_part + (static_cast<size_t>(jb) * S.groups + gi) * kBlockBytes, kBlockBytes, bar_wfull + 8 * st, pol);
+      for (int k = 0; k < sw.nseg; ++k) {
+        int ra, rb;
+        seg_range(sw, k, ra, rb);
+        const int jb = static_cast<int>(static_cast<unsigned>(ra) / static_cast<unsigned>(g.ng));
+        int gi = ra - jb * g.ng;
+#pragma unroll 1
+        for (int r = ra; r < rb; ++r, ++gi) {
+          if (it > 0) mbar_wait(bar_wempty + 8 * st, (it - 1) & 1);
+          // at most `inflight` records outstanding per SM (the stage of copy n - inflight has not been reused yet)
+          if (issued >= static_cast<uint32_t>(p.inflight)) mbar_wait(bar_wfull + 8 * lag_st, lag_it & 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bar_wfull + 8 * st, kBlockBytes);
+            bulk_g2s(smem0 + st * kStmStage, rec_part + (static_cast<size_t>(jb) * S.groups + gi) * kBlockBytes, kBlockBytes, bar_wfull + 8 * st, pol);
+          }
+          __syncwarp();
+          if (++st == NS) { st = 0; ++it; }
+          if (++issued > static_cast<uint32_t>(p.inflight)) {
+            if (++lag_st == NS) { lag_st = 0; ++lag_it; }
+          }
         }
-        __syncwarp();
-        if (++st == NS) { st = 0; ++it; }
-        if (++gi == g.ng) { gi = 0; ++jb; }
       }
     }
   } else if (warp == kMmaWarp) {
@@ -410,33 +529,34 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 6), 1) stream_kernel(const __
       mbar_wait(bar_xb, i & 1);   // B operand rows written (generic proxy) and fenced by the workers
       tc_fence_after();
       if (g.active) {
-        int jb = g.r0 / g.ng, gi = g.r0 - jb * g.ng;
-        bool first = true;
+        const SegWalk sw = seg_walk(g);
 #pragma unroll 1
-        for (int r = g.r0; r < g.r1; ++r) {
-          if (first && duse > 0) mbar_wait(bar_dfree + 8 * d, (duse - 1) & 1);   // accumulator read back by the epilogue group
-          mbar_wait(bar_afull + 8 * a, ause & 1);
-          tc_fence_after();
-          const uint32_t td = tmem + kStmDCol0 + d * kStmN, ta = tmem + a * 64;
-          const uint64_t bdesc0 = desc_hi | static_cast<uint64_t>(((xb + gi * (NR * 256)) >> 4) & 0x3FFF);
-          const bool last = (gi == g.ng - 1) || (r == g.r1 - 1);
-          if (elect_one()) {
+        for (int k = 0; k < sw.nseg; ++k) {
+          int ra, rb;
+          seg_range(sw, k, ra, rb);
+          int gi = ra - static_cast<int>(static_cast<unsigned>(ra) / static_cast<unsigned>(g.ng)) * g.ng;
+          if (duse > 0) mbar_wait(bar_dfree + 8 * d, (duse - 1) & 1);   // accumulator read back by the epilogue group
+          const uint32_t td = tmem + kStmDCol0 + d * kStmN;
+#pragma unroll 1
+          for (int r = ra; r < rb; ++r, ++gi) {
+            mbar_wait(bar_afull + 8 * a, ause & 1);
+            tc_fence_after();
+            const uint32_t ta = tmem + a * 64;
+            const uint64_t bdesc0 = desc_hi | static_cast<uint64_t>(((xb + gi * (NR * 256)) >> 4) & 0x3FFF);
+            if (elect_one()) {
 #pragma unroll
-            for (int s = 0; s < 8; ++s) tc_mma_ts(td, ta + 8 * s, bdesc0 + s * ((NR * 32) >> 4), idesc, (first && s == 0) ? 0u : 1u);
-            tc_commit(bar_afree + 8 * a);
-            if (last) tc_commit(bar_dfull + 8 * d);
+              for (int s = 0; s < 8; ++s) tc_mma_ts(td, ta + 8 * s, bdesc0 + s * ((NR * 32) >> 4), idesc, (r == ra && s == 0) ? 0u : 1u);
+              tc_commit(bar_afree + 8 * a);
+              if (r == rb - 1) tc_commit(bar_dfull + 8 * d);
+            }
+            __syncwarp();
+            if (++a == kStmABufs) { a = 0; ++ause; }
           }
-          __syncwarp();
-          first = false;
-          if (last) {
-            first = true;
-            if (++d == kStmDBufs) { d = 0; ++duse; }
-          }
-          if (++a == kStmABufs) { a = 0; ++ause; }
-          if (++gi == g.ng) { gi = 0; ++jb; }
+          if (++d == kStmDBufs) { d = 0; ++duse; }
         }
         if (elect_one()) tc_commit(bar_stepdone);   // arrives when every MMA of this step has read its operands
         __syncwarp();
+        STM_TRACE(i, 10);
       } else {
         if (lane == 0) mbar_arrive(bar_stepdone);
         __syncwarp();
@@ -449,9 +569,7 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 6), 1) stream_kernel(const __
     // No fences, no counters: every 8-byte word carries the launch's tag, a reader retries until the tag matches.
     const int q = warp & 3;
     const int L128 = 32 * q + lane;
-    const int tid = (warp - kEpiWarp0) * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(32 * q) << 16;
-    const uint32_t s_part = misc;
     int d = 0, duse = 0;
     uint32_t tag = 0;
     bool have_tag = false;
@@ -461,169 +579,180 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 6), 1) stream_kernel(const __
       const StepGeom g = step_geom(S, cta);
       if (!g.active) continue;
       const int n_end = S.part_col_begin[g.part + 1];
-      // Pass 0 walks the segments as their accumulators complete: D -> own slot (never waits), and a reducer TRIES to
-      // finish its block if the other contributors' slots are already there.  Pass 1 finishes what was left pending,
-      // now waiting for the slots.  Writing everything before waiting for anything keeps contributors from queueing
-      // behind each other (member t's last segment is what member t + 1's first block waits for).
-      unsigned long long pending = 0ull;
+      const SegWalk sw = seg_walk(g);
+      const bool tp = S.tp_world > 1;
+      // Every segment's accumulator goes to its slot as soon as it completes -- nothing ever waits before that, so
+      // contributors cannot queue behind each other.  A block this CTA reduces stays PENDING until all its contributors'
+      // slots carry this launch's tag; pending blocks are looked at (one non-blocking look each) while the group waits for
+      // the next accumulator, and after the last segment until none is left.
+      unsigned long long pending = 0ull, pushed_mask = 0ull;
+
+      // who contributes to a segment's block: per slice, the team members whose runs overlap it (fixed order); am I its
+      // reducer.  Integer divisions galore, so every lane works this out for two segments while the warp has nothing else to
+      // do (before the step's first accumulator) and parks it in shared memory: one 16-byte load per look afterwards.
+      const uint32_t seg_tab = smem0 + p.misc_off + q * 1024;
+      for (int k = lane; k < sw.nseg && k < 64; k += 32) {
+        int ra, rb;
+        seg_range(sw, k, ra, rb);
+        const int jb = static_cast<int>(static_cast<unsigned>(ra) / static_cast<unsigned>(g.ng));
+        const int gb = S.part_block_begin[g.part] + jb;
+        int total = 0, myslot = 0;
+        unsigned gs0 = 0;
+        for (int sl = 0; sl < S.c; ++sl) {
+          const unsigned gs1 = static_cast<unsigned>((sl + 1) * S.groups) / static_cast<unsigned>(S.c);
+          const int ngs = static_cast<int>(gs1 - gs0);
+          gs0 = gs1;
+          const int Rp = g.blocks_p * ngs;
+          const int lo = round_owner(jb * ngs, Rp, g.Tp), hi = round_owner((jb + 1) * ngs - 1, Rp, g.Tp);
+          if (sl == g.slice) myslot = total + (g.t - lo);
+          total += hi - lo + 1;
+        }
+        // the reducer: in slice (block mod c), the member that holds the block's last round there (spread over the slices)
+        const bool reducer = static_cast<unsigned>(g.slice) == static_cast<unsigned>(gb) % static_cast<unsigned>(S.c) && rb == (jb + 1) * g.ng;
+        sts128u(seg_tab + 16 * k, make_uint4(static_cast<uint32_t>(jb), static_cast<uint32_t>(gb), static_cast<uint32_t>(total),
+                                             static_cast<uint32_t>(myslot) | (reducer ? 0x80000000u : 0u)));
+      }
+      __syncwarp();
+      auto block_info = [&](int k, int &jb, int &gb, int &total, int &myslot, bool &reducer) {
+        const uint4 e = lds128(seg_tab + 16 * k);
+        jb = static_cast<int>(e.x);
+        gb = static_cast<int>(e.y);
+        total = static_cast<int>(e.z);
+        myslot = static_cast<int>(e.w & 0x7FFFFFFFu);
+        reducer = (e.w >> 31) != 0u;
+      };
+
+      // add the block's slots: stage 1 this GPU's contributors, stage 2 (tensor parallelism) the ranks' sums.  Returns false
+      // if something is missing (`wait` = false: one look).
+      auto sum_block = [&](int gb, int total, unsigned long long bit, float (&acc)[MB]) -> bool {
+        const bool pushed = (pushed_mask & bit) != 0ull;
+        if (!pushed) {
+#pragma unroll
+          for (int m = 0; m < MB; ++m) acc[m] = 0.f;
+          if (!ll_sum<false, MB>(S.slots + static_cast<size_t>(gb) * S.max_slots * (M * 128) + L128, total, M, tag, false, acc)) return false;
+        }
+        if (tp) {
+          // my block sum goes to every rank (mine included), then the `world` sums are added in rank order -- every rank
+          // computes the same bits.  Nothing waits before the push.  Buffers alternate with the launch parity: a rank that
+          // is one launch ahead writes the other half while this one is still reading.
+          const size_t blk = (static_cast<size_t>(tag & 1u) * S.blocks_total + gb) * S.tp_world;
+          if (!pushed) {
+            for (int rk = 0; rk < S.tp_world; ++rk) {
+              uint2 *dst = S.tp_slots[rk] + (blk + S.tp_rank) * (M * 128) + L128;
+#pragma unroll
+              for (int m = 0; m < MB; ++m)
+                if (m < M) st_relaxed_sys_v2(dst + m * 128, __float_as_uint(acc[m]), tag);
+            }
+            pushed_mask |= bit;
+          }
+#pragma unroll
+          for (int m = 0; m < MB; ++m) acc[m] = 0.f;
+          if (!ll_sum<true, MB>(S.tp_slots[S.tp_rank] + blk * (M * 128) + L128, S.tp_world, M, tag, false, acc)) return false;
+        }
+        return true;
+      };
+
+      // round once to T, bias, epilogue, publish for the next step
+      auto finish_block = [&](int jb, int gb, float (&acc)[MB]) {
+        if (warp == kEpiWarp0) STM_TRACE(i, 9);
+        const int n = S.part_col_begin[g.part] + jb * kBlockN + L128;
+        const bool ok = n < n_end;
+        const bool add_res = S.epi_op == PARO_EPI_ADD_RESIDUAL;
+#pragma unroll
+        for (int m = 0; m < MB; ++m) {
+          float sq = 0.f;
+          if (m < M && ok) {
+            T t = Traits<T>::from_float(acc[m]);
+            if (S.bias) t = Traits<T>::from_float(Traits<T>::to_float(t) + Traits<T>::to_float(static_cast<const T *>(S.bias)[n]));  // plugin.py:309-310
+            const int64_t o = static_cast<int64_t>(m) * S.N + n;
+            if (S.y) static_cast<T *>(S.y)[o] = t;
+            if (add_res) {
+              t = Traits<T>::from_float(Traits<T>::to_float(t) + Traits<T>::to_float(static_cast<const T *>(S.res_in)[o]));
+              static_cast<T *>(S.res_out)[o] = t;
+              const float hf = Traits<T>::to_float(t);
+              sq = hf * hf;
+            }
+            if (S.out_ll) st_relaxed_v2(S.out_ll + o, T_to_bits<T>(t), tag);   // what the next step consumes
+          }
+          acc[m] = sq;
+        }
+        if (add_res && S.stats_ll) {
+          // per-row sum of h^2 over this warp's 32 columns (butterfly): one {sum, tag} word per (block, warp, row)
+#pragma unroll
+          for (int m = 0; m < MB; ++m) {
+            if (m < M) {
+              float sm = acc[m];
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(0xFFFFFFFFu, sm, o);
+              if (lane == 0) st_relaxed_v2(S.stats_ll + (gb * 4 + q) * M + m, __float_as_uint(sm), tag);
+            }
+          }
+        }
+      };
+
 #pragma unroll 1
-      for (int pass = 0; pass < 2; ++pass) {
-        if (pass == 1 && pending == 0ull) break;
-        int r = g.r0, seg = 0;
+      for (int k = 0; k <= sw.nseg; ++k) {     // k == nseg: drain what is still pending
+        // ---- wait for D of segment k; meanwhile (except before the step's last segment, whose D must not be kept waiting)
+        // look at the pending blocks, one non-blocking look each
 #pragma unroll 1
-        while (r < g.r1) {
-          const int jb = r / g.ng;
-          int rb = (jb + 1) * g.ng;
-          if (rb > g.r1) rb = g.r1;
-          const unsigned long long bit = seg < 64 ? 1ull << seg : 0ull;
-          // ---- who contributes to this block: per slice, the team members whose runs overlap it (fixed order)
-          const int gb = S.part_block_begin[g.part] + jb;
-          int total = 0, myslot = 0;
-          for (int s = 0; s < S.c; ++s) {
-            const int ngs = (s + 1) * S.groups / S.c - s * S.groups / S.c;
-            const int Rp = g.blocks_p * ngs;
-            const int lo = round_owner(jb * ngs, Rp, g.Tp), hi = round_owner((jb + 1) * ngs - 1, Rp, g.Tp);
-            if (s == g.slice) myslot = total + (g.t - lo);
-            total += hi - lo + 1;
+        for (;;) {
+          if (k < sw.nseg) {
+            if (mbar_try_wait(bar_dfull + 8 * d, duse & 1)) break;
+            if (k + 1 == sw.nseg || pending == 0ull) {
+              mbar_wait(bar_dfull + 8 * d, duse & 1);
+              break;
+            }
+          } else if (pending == 0ull) {
+            break;
           }
-          const bool reducer = g.slice == S.c - 1 && rb == (jb + 1) * g.ng;   // holds the block's last round
-          float acc[16];
-          bool doit = false, wait = false;
-          if (pass == 0) {
-            // ---- D of segment [r, rb) of block jb
-            mbar_wait(bar_dfull + 8 * d, duse & 1);
-            tc_fence_after();
-            if (!have_tag) {   // the workers are past griddepcontrol.wait: the previous launch has bumped the epoch
-              tag = ld_relaxed_u32(p.sync) + 1u;
-              have_tag = true;
-            }
-            uint32_t v[16];
-            if (M <= 8) tc_ld8(tmem + lane_base + kStmDCol0 + d * kStmN, v);
-            else tc_ld16(tmem + lane_base + kStmDCol0 + d * kStmN, v);
-            tc_wait_ld();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_dfree + 8 * d);
-            if (++d == kStmDBufs) { d = 0; ++duse; }
-            if (warp == kEpiWarp0) STM_TRACE(i, 7);
-#pragma unroll
-            for (int m = 0; m < 16; ++m) acc[m] = __uint_as_float(v[m]);
-            if (total > 1) {
-              uint2 *slot = S.slots + (static_cast<size_t>(gb) * S.max_slots + myslot) * (M * 128) + L128;
-#pragma unroll
-              for (int m = 0; m < 16; ++m)
-                if (m < M) st_relaxed_v2(slot + m * 128, v[m], tag);
-            }
-            doit = reducer;
-            wait = bit == 0ull;   // beyond the pending mask: finish in place
-          } else {
-            doit = (pending & bit) != 0ull;
-            wait = true;
-          }
-          if (doit && total > 1) {
-            // ---- slots 0 .. total - 1 in order (mine is the last one); without `wait` one look, give up if anything is missing
-            const uint2 *src = S.slots + static_cast<size_t>(gb) * S.max_slots * (M * 128) + L128;
-#pragma unroll
-            for (int m = 0; m < 16; ++m) acc[m] = 0.f;
-            bool ready = true;
-            if (M == 1) {
-              for (int k0 = 0; k0 < total && ready; k0 += 8) {   // 8 contributors in flight
-                uint2 w[8];
-                bool ok;
-                do {
-                  ok = true;
-#pragma unroll
-                  for (int kk = 0; kk < 8; ++kk)
-                    if (k0 + kk < total) {
-                      w[kk] = ld_relaxed_v2(src + (k0 + kk) * 128);
-                      ok = ok && w[kk].y == tag;
-                    }
-                } while (!ok && wait);
-                ready = ok;
-#pragma unroll
-                for (int kk = 0; kk < 8; ++kk)
-                  if (k0 + kk < total) acc[0] += __uint_as_float(w[kk].x);
+#pragma unroll 1
+          for (int kk = 0; kk < sw.nseg; ++kk) {
+            const unsigned long long pb = 1ull << kk;
+            if (pending & pb) {
+              int jb, gb, total, myslot;
+              bool reducer;
+              block_info(kk, jb, gb, total, myslot, reducer);
+              float acc[MB];
+              if (sum_block(gb, total, pb, acc)) {
+                finish_block(jb, gb, acc);
+                pending &= ~pb;
               }
-            } else {
-              for (int k = 0; k < total && ready; ++k) {   // one contributor at a time, 8 rows in flight
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                  if (8 * h < M && ready) {
-                    uint2 w[8];
-                    bool ok;
-                    do {
-                      ok = true;
-#pragma unroll
-                      for (int m = 0; m < 8; ++m)
-                        if (8 * h + m < M) {
-                          w[m] = ld_relaxed_v2(src + (k * M + 8 * h + m) * 128);
-                          ok = ok && w[m].y == tag;
-                        }
-                    } while (!ok && wait);
-                    ready = ok;
-#pragma unroll
-                    for (int m = 0; m < 8; ++m)
-                      if (8 * h + m < M) acc[8 * h + m] += __uint_as_float(w[m].x);
-                  }
-                }
-              }
-            }
-            // the four warps must agree (they share the statistics reduction below): any warp not ready defers the block
-            ready = __all_sync(0xFFFFFFFFu, ready);
-            if (lane == 0) sts32(s_part + 256 + 4 * q, ready ? 1u : 0u);
-            named_bar_sync(2, 128);
-            ready = (lds32(s_part + 256) & lds32(s_part + 260) & lds32(s_part + 264) & lds32(s_part + 268)) != 0u;
-            named_bar_sync(2, 128);
-            if (!ready) {
-              pending |= bit;
-              doit = false;
             }
           }
-          if (doit) {
-            if (warp == kEpiWarp0 && total > 1) STM_TRACE(i, 9);
-            // ---- finish the block
-            const int n = S.part_col_begin[g.part] + jb * kBlockN + L128;
-            const bool ok = n < n_end;
-            const bool add_res = S.epi_op == PARO_EPI_ADD_RESIDUAL;
+        }
+        if (k == sw.nseg) break;
+        tc_fence_after();
+        if (warp == kEpiWarp0) STM_TRACE(i, 8);
+        if (!have_tag) {   // the workers are past griddepcontrol.wait: the previous launch has bumped the epoch
+          tag = ld_relaxed_u32(p.sync) + 1u;
+          have_tag = true;
+        }
+        uint32_t v[16];
+        if constexpr (MB == 1) tc_ld1(tmem + lane_base + kStmDCol0 + d * kStmN, v[0]);
+        else if constexpr (MB == 4) tc_ld4(tmem + lane_base + kStmDCol0 + d * kStmN, v);
+        else if (M <= 8) tc_ld8(tmem + lane_base + kStmDCol0 + d * kStmN, v);
+        else tc_ld16(tmem + lane_base + kStmDCol0 + d * kStmN, v);
+        tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dfree + 8 * d);
+        if (++d == kStmDBufs) { d = 0; ++duse; }
+        if (warp == kEpiWarp0) STM_TRACE(i, 7);
+        int jb, gb, total, myslot;
+        bool reducer;
+        block_info(k, jb, gb, total, myslot, reducer);
+        float acc[MB];
 #pragma unroll
-            for (int m = 0; m < 16; ++m) {
-              float sq = 0.f;
-              if (m < M && ok) {
-                T t = Traits<T>::from_float(acc[m]);
-                if (S.bias) t = Traits<T>::from_float(Traits<T>::to_float(t) + Traits<T>::to_float(static_cast<const T *>(S.bias)[n]));  // plugin.py:309-310
-                const int64_t o = static_cast<int64_t>(m) * S.N + n;
-                if (S.y) static_cast<T *>(S.y)[o] = t;
-                if (add_res) {
-                  t = Traits<T>::from_float(Traits<T>::to_float(t) + Traits<T>::to_float(static_cast<const T *>(S.res_in)[o]));
-                  static_cast<T *>(S.res_out)[o] = t;
-                  const float hf = Traits<T>::to_float(t);
-                  sq = hf * hf;
-                }
-                if (S.out_ll) st_relaxed_v2(S.out_ll + o, T_to_bits<T>(t), tag);   // what the next step consumes
-              }
-              acc[m] = sq;
-            }
-            if (add_res && S.stats_ll) {
-              // per-row sum of h^2 over this block's 128 columns: butterfly inside each warp, then the 4 warps in order
+        for (int m = 0; m < MB; ++m) acc[m] = __uint_as_float(v[m]);
+        if (total == 1 && !tp) {
+          finish_block(jb, gb, acc);     // nobody else contributes: straight from the accumulator
+        } else {
+          uint2 *slot = S.slots + (static_cast<size_t>(gb) * S.max_slots + myslot) * (M * 128) + L128;
 #pragma unroll
-              for (int m = 0; m < 16; ++m) {
-                if (m < M) {
-                  float s = acc[m];
-#pragma unroll
-                  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-                  if (lane == 0) sts_f32(s_part + (q * 16 + m) * 4, s);
-                }
-              }
-              named_bar_sync(2, 128);
-              if (tid < M) {
-                const float s = ((lds_f32(s_part + tid * 4) + lds_f32(s_part + (16 + tid) * 4)) + lds_f32(s_part + (32 + tid) * 4)) + lds_f32(s_part + (48 + tid) * 4);
-                st_relaxed_v2(S.stats_ll + gb * M + tid, __float_as_uint(s), tag);
-              }
-              named_bar_sync(2, 128);   // the partial sums are reused by the next segment
-            }
-          }
-          ++seg;
-          r = rb;
+          for (int m = 0; m < MB; ++m)
+            if (m < M) st_relaxed_v2(slot + m * 128, v[m], tag);
+          if (reducer) pending |= 1ull << k;
+          if (warp == kEpiWarp0 && k + 1 == sw.nseg) STM_TRACE(i, 11);
         }
       }
       if (warp == kEpiWarp0) STM_TRACE(i, 6);
@@ -666,9 +795,14 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 6), 1) stream_kernel(const __
       if (i > 0) mbar_wait(bar_stepdone, (i - 1) & 1);
       if (mine) {
         if (wi == 0) STM_TRACE(i, 2);
-        if (M == 1) stm_prologue<T, 1>(S, M, NR, rm, g, ntasks, nq, wi, p.rot_warps, lane, rot, xb, tag);
-        else if (M == 2) stm_prologue<T, 2>(S, M, NR, rm, g, ntasks, nq, wi, p.rot_warps, lane, rot, xb, tag);
-        else stm_prologue<T, 4>(S, M, NR, rm, g, ntasks, nq, wi, p.rot_warps, lane, rot, xb, tag);
+        if constexpr (MB == 1) {
+          stm_prologue<T, 1>(S, M, NR, rm, g, ntasks, nq, wi, p.rot_warps, lane, rot, xb, tag);
+        } else if constexpr (MB == 4) {
+          if (M == 2) stm_prologue<T, 2>(S, M, NR, rm, g, ntasks, nq, wi, p.rot_warps, lane, rot, xb, tag);
+          else stm_prologue<T, 4>(S, M, NR, rm, g, ntasks, nq, wi, p.rot_warps, lane, rot, xb, tag);
+        } else {
+          stm_prologue<T, 4>(S, M, NR, rm, g, ntasks, nq, wi, p.rot_warps, lane, rot, xb, tag);
+        }
         fence_proxy_async_smem();  // B rows were written through the generic proxy, tcgen05.mma reads them through the async proxy
       }
       __syncwarp();
@@ -753,7 +887,7 @@ int stream_trace_read(unsigned long long *host, int max_ctas) {
 
 // ------------------------------------------------------------------ host side: plan (pure, cached), carve-up, launch
 struct StmKnobs {
-  int sets, stages, force_c, no_pdl, trace, verbose, b8;
+  int sets, stages, force_c, no_pdl, trace, verbose, b8, inflight;
 };
 static const StmKnobs &stm_knobs() {
   static const StmKnobs k = [] {
@@ -762,14 +896,14 @@ static const StmKnobs &stm_knobs() {
       return v && *v ? atoi(v) : dflt;
     };
     StmKnobs x;
-    x.sets = env("PARO_DECODE_SETS", 5);
+    x.sets = kStmSets;
     x.stages = env("PARO_DECODE_STAGES", 0);
     x.force_c = env("PARO_DECODE_C", 0);
     x.no_pdl = env("PARO_NO_PDL", 0);
     x.trace = env("PARO_DECODE_TRACE", 0);
     x.verbose = env("PARO_DECODE_VERBOSE", 0);
     x.b8 = env("PARO_DECODE_B8", 1);
-    if (x.sets < 4 || x.sets > 6) x.sets = 5;
+    x.inflight = env("PARO_DECODE_INFLIGHT", 6);
     return x;
   }();
   return k;
@@ -854,6 +988,8 @@ static bool stm_choose_plan(const Layout &L, int M, int sets, int ctas, int forc
         if (total > pl.max_slots) pl.max_slots = total;
       }
     }
+    if (static_cast<long long>(L.blocks_total) * pl.ng_max * (ctas + 1) >= (1ll << 31)) continue;   // the kernel's 32-bit round arithmetic
+    if (pl.max_rounds / (L.groups / c) + 3 > 64) continue;   // segments of a CTA's run: the epilogue's pending mask is 64 bits
     const int passes = (pl.ng_max * nq + 4 * sets - 1) / (4 * sets);
     long cost = static_cast<long>(pl.max_rounds) * 8 + passes * 24 + pl.max_slots;
     if (nst_room < 2 * sets) cost += cost / 4;
@@ -916,9 +1052,9 @@ struct StepWs { size_t stats_off, out_off, slots_off, end; };
 static StepWs stm_step_ws(const Layout &L, const StepPlan &pl, int M, size_t base, bool consumed) {
   StepWs w;
   w.stats_off = base;
-  w.out_off = w.stats_off + (consumed ? (static_cast<size_t>(L.blocks_total) * M * 8 + 255) / 256 * 256 : 0);
+  w.out_off = w.stats_off + (consumed ? (static_cast<size_t>(L.blocks_total) * 4 * M * 8 + 255) / 256 * 256 : 0);
   w.slots_off = w.out_off + (consumed ? (static_cast<size_t>(M) * L.N * 8 + 255) / 256 * 256 : 0);
-  w.end = w.slots_off + (pl.max_slots > 1 ? static_cast<size_t>(L.blocks_total) * pl.max_slots * M * 1024 : 0);
+  w.end = w.slots_off + static_cast<size_t>(L.blocks_total) * pl.max_slots * M * 1024;
   w.end = (w.end + 255) / 256 * 256;
   return w;
 }
@@ -942,9 +1078,9 @@ size_t stream_workspace_bytes(const Layout &L, int64_t max_m) {
   return need;
 }
 
-template <typename T, int SETS>
+template <typename T, int SETS, int MB>
 static int stm_launch(StreamParams &p, int max_ng, int ctas, cudaStream_t stream) {
-  auto kern = stream_kernel<T, SETS>;
+  auto kern = stream_kernel<T, SETS, MB>;
   const StmKnobs &kn = stm_knobs();
   const int M = p.M;
   p.nrows_b = stm_b_rows(M);
@@ -961,6 +1097,7 @@ static int stm_launch(StreamParams &p, int max_ng, int ctas, cudaStream_t stream
     nst = nst / SETS * SETS;
     if (nst >= SETS) {
       p.nstages = nst;
+      p.inflight = kn.inflight < 1 ? 1 : kn.inflight > nst - 1 ? nst - 1 : kn.inflight;
       p.rot_warps = rw;
       p.xb_off = (nst * kStmStage + 127) / 128 * 128;
       p.rot_off = p.xb_off + xb_bytes;
@@ -1062,6 +1199,11 @@ int stream_forward(const HostStep *steps, int n, int64_t M, void *workspace, siz
       S.part_block_begin[k] = L.part_block_begin[k];
       S.part_cta_begin[k] = pl.part_cta_begin[k];
     }
+    if (h.tp && h.tp->world > 1) {
+      S.tp_world = h.tp->world;
+      S.tp_rank = h.tp->rank;
+      for (int r = 0; r < h.tp->world; ++r) S.tp_slots[r] = static_cast<uint2 *>(h.tp->peer_slots[r]);
+    }
     S.x_ld = h.x_op == PARO_XOP_SILU_MUL ? 2 * L.K : L.K;
     if (h.x) {
       S.x = h.x;
@@ -1074,7 +1216,7 @@ int stream_forward(const HostStep *steps, int n, int64_t M, void *workspace, siz
       if (P.N != S.x_ld) { set_error("chain: step %d produces %d columns, step %d consumes %d", i - 1, P.N, i, S.x_ld); return PARO_EINVAL; }
       S.x_ll = P.out_ll;
       S.stats_in = P.stats_ll;
-      S.stats_in_blocks = P.blocks_total;
+      S.stats_in_blocks = 4 * P.blocks_total;   // one partial sum per (block, epilogue warp)
     }
     if (h.epi_op == PARO_EPI_ADD_RESIDUAL && (!h.res_in || !h.res_out)) { set_error("chain: step %d: ADD_RESIDUAL needs residual_in and residual_out", i); return PARO_EINVAL; }
     if (h.epi_op == PARO_EPI_STORE && !h.y && !consumed) { set_error("chain: step %d has no output", i); return PARO_EINVAL; }
@@ -1082,11 +1224,9 @@ int stream_forward(const HostStep *steps, int n, int64_t M, void *workspace, siz
     if (pl.ng_max > max_ng) max_ng = pl.ng_max;
   }
   const bool bf16 = dtype == PARO_BF16;
-  switch (kn.sets) {
-    case 4: return bf16 ? stm_launch<__nv_bfloat16, 4>(p, max_ng, sms, stream) : stm_launch<__half, 4>(p, max_ng, sms, stream);
-    case 6: return bf16 ? stm_launch<__nv_bfloat16, 6>(p, max_ng, sms, stream) : stm_launch<__half, 6>(p, max_ng, sms, stream);
-    default: return bf16 ? stm_launch<__nv_bfloat16, 5>(p, max_ng, sms, stream) : stm_launch<__half, 5>(p, max_ng, sms, stream);
-  }
+  if (p.M == 1) return bf16 ? stm_launch<__nv_bfloat16, kStmSets, 1>(p, max_ng, sms, stream) : stm_launch<__half, kStmSets, 1>(p, max_ng, sms, stream);
+  if (p.M <= 4) return bf16 ? stm_launch<__nv_bfloat16, kStmSets, 4>(p, max_ng, sms, stream) : stm_launch<__half, kStmSets, 4>(p, max_ng, sms, stream);
+  return bf16 ? stm_launch<__nv_bfloat16, kStmSets, 16>(p, max_ng, sms, stream) : stm_launch<__half, kStmSets, 16>(p, max_ng, sms, stream);
 }
 
 // single linear (paro_linear_forward, M <= 16)

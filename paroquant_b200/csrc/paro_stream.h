@@ -14,6 +14,7 @@ struct HostStep {
   void *res_out;
   const void *norm_w;
   float eps;
+  const paro_tp_info *tp;
 };
 
 }  // namespace paro

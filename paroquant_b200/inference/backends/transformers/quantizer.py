@@ -7,8 +7,8 @@ unquantised layers are left alone.  Differences from the reference, both deliber
 with ``paroquant_b200.checkpoint_io``; bf16 is accepted next to fp16 (the fused kernels compute in either, the
 reference's AutoAWQ GEMM is fp16 only, quantizer.py:78-82).
 
-Importing this module registers the config and the quantizer with transformers (it is not imported by the package
-``__init__`` so that the kernels stay usable without transformers' quantizer registry).
+Importing this module registers the config and the quantizer with transformers; the package ``__init__`` imports it when
+transformers is installed (``register()``), so a plain ``from_pretrained`` finds it.
 """
 from __future__ import annotations
 

@@ -229,3 +229,29 @@ def test_large_m_vs_oracle(PK, oracle):
     y = k(x.cuda()).float().cpu().numpy()
     ref = oracle.linear(x.float().numpy(), L.numpy_dict(), "bfloat16")
     assert oracle.rel_err(y, ref) < TOL
+
+
+@pytest.mark.parametrize("name,K,parts", [("qkv", 4096, [4096, 1024, 1024]), ("o", 4096, [4096]), ("gate_up", 4096, [14336, 14336]),
+                                          ("down", 14336, [4096]), ("llama2_down", 11008, [4096])])
+def test_prefill_4096_vs_oracle_samples(PK, oracle, name, K, parts):
+    """The batch bench.py's `prefill` section reports (4096 tokens, Llama-3-8B shapes, plus K = 11008): sampled token rows
+    x sampled output columns against the oracle (its rotate on the sampled rows, its dequant on the sampled columns, its
+    fp32 GEMM), every partition and the last partial token tile included."""
+    M = 4096
+    L = make_synthetic_layer(K, parts, seed=97)
+    k = PK.from_buffers(L.to("cuda"), torch.bfloat16, check_pairs=False, max_m=M)
+    x = make_synthetic_activations(M, K, seed=98)
+    y = k(x.cuda()).float().cpu().numpy()
+    rows = np.array([0, 1, 255, 256, 1023, 2048, 4095])
+    d = L.numpy_dict()
+    W = None
+    n0 = 0
+    for p, n in enumerate(parts):
+        cols = n0 + np.array(sorted({0, 1, 127, 128, n // 2 + 5, n - 129, n - 1}))
+        xr = oracle.c_rotate(x[rows].float().numpy(), d["pairs"][p], d["theta"][p], d["channel_scales"][p], 128, "bfloat16")
+        if W is None:
+            W = oracle.c_dequant(d["qweight"], d["qzeros"], d["scales"], 128, "bfloat16")
+        ref = oracle.c_gemm(xr, np.ascontiguousarray(W[:, cols]), None, "bfloat16")
+        got = y[np.ix_(rows, cols)]
+        assert oracle.rel_err(got, ref) < TOL, (name, p)
+        n0 += n

@@ -24,7 +24,7 @@ from paroquant_b200.linear import ParoLinearKernel  # noqa: E402
 H, KV, I = 4096, 1024, 14336
 SH = {"o": (H, [H]), "gate_up": (H, [I, I]), "down": (I, [H]), "qkv": (H, [H, KV, KV])}
 NAMES = ["before pdl wait", "step start", "flag passed", "B operand ready", "first record", "rounds done", "epilogue done",
-         "last D read", "last counter", "last fix-up", "-", "-"]
+         "last D read", "last D full", "last fix-up", "MMAs issued", "pass 1 start"]
 
 
 def dump(nsteps):
@@ -34,9 +34,14 @@ def dump(nsteps):
     t = torch.tensor(list(buf), dtype=torch.float64).view(nct, nst, nsl)
     for i in range(nsteps):
         print(f" step {i}:   {'CTA 0':>8s} {'median':>8s} {'max':>8s}")
-        for sl in range(10):
+        for sl in range(12):
             col = t[:, i, sl]
             print(f"   {NAMES[sl]:16s} {int(col[0]):8d} {int(col.median()):8d} {int(col.max()):8d}")
+        order = torch.argsort(t[:, i, 6], descending=True)
+        pick = [int(v) for v in order[:4]] + [int(order[len(order) // 2])]
+        print("   rows (slowest 4 CTAs by epilogue done, then the median one): cta | " + " | ".join(n.split()[-1] for n in NAMES))
+        for c in pick:
+            print(f"   cta {c:3d}: " + " ".join(f"{int(v):7d}" for v in t[c, i]))
 
 
 def main():
