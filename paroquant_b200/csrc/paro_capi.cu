@@ -138,9 +138,16 @@ int paro_linear_forward(const paro_linear_shape *shape, const void *packed, cons
     return PARO_EINVAL;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (M <= small_m_max()) {   // one persistent CTA per SM (paro_stream.cu)
-    static const bool v1 = [] { const char *v = getenv("PARO_DECODE_V1"); return v && *v && atoi(v) != 0; }();
-    if (v1) return decode_forward(*shape, L, packed, x, M, bias, y, st);
+  if (M <= small_m_max()) {
+    // A single linear: the cluster kernel (paro_decode.cu: K slices reduced through distributed shared memory) has the shorter
+    // tail -- measured 7.4 / 9.9 / 22.0 / 15.6 us on the Llama-3-8B shapes at M = 1 against 11.1 / 12.3 / 24.3 / 16.2 us for
+    // the chain kernel run as a one-step chain, whose cross-CTA sums travel through L2.  The chain kernel takes over where the
+    // cluster kernel has no launch plan (very long K) and for chains / tensor-parallel steps (paro_chain_forward).
+    static const bool stream_only = [] { const char *v = getenv("PARO_DECODE_STREAM"); return v && *v && atoi(v) != 0; }();
+    if (!stream_only) {
+      const int rc = decode_forward(*shape, L, packed, x, M, bias, y, st);
+      if (rc != PARO_EUNSUPPORTED) return rc;
+    }
     return stream_linear_forward(*shape, L, packed, x, M, bias, y, workspace, workspace_bytes, st);
   }
   const size_t head = stream_sync_bytes(L);   // never touched by the large-M path

@@ -27,6 +27,9 @@
 // Numerics: x_rot as paro_rotate.cu; W = T((q - z) * T(s)) with ONE rounding (the operand Marlin / AWQ
 // form); fp32 accumulation in TMEM; one rounding to T; bias added in T (plugin.py:309-310).
 #include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
 
 #include "paro_tc_common.cuh"
 
@@ -418,6 +421,14 @@ static int dec_env_int(const char *name, int dflt) {
   const char *v = getenv(name);
   return v && *v ? atoi(v) : dflt;
 }
+// environment knobs are read ONCE per process (every launch used to pay half a dozen getenv calls)
+struct DecKnobs { int stages, no_cluster, force_c, verbose, no_pdl, trace, sets; };
+static const DecKnobs &dec_knobs() {
+  static const DecKnobs k = {dec_env_int("PARO_DECODE_STAGES", 0), dec_env_int("PARO_NO_CLUSTER", 0), dec_env_int("PARO_DECODE_C", 0),
+                             dec_env_int("PARO_DECODE_VERBOSE", 0), dec_env_int("PARO_NO_PDL", 0), dec_env_int("PARO_DECODE_TRACE", 0),
+                             dec_env_int("PARO_DECODE_SETS", 5)};
+  return k;
+}
 
 struct DecPlan {
   int c, c_shift, ranges, grid;
@@ -481,7 +492,7 @@ static bool dec_carve_with(const DecPlan &plan, int M, int rot_bytes, int sets, 
   const int fixed = xb_bytes + rot_total + recv + bar_bytes + 128;
   int nst = (kDecSmemLimit - fixed) / kDecStage;
   if (nst > kDecMaxStages) nst = kDecMaxStages;
-  const int want = dec_env_int("PARO_DECODE_STAGES", 0);
+  const int want = dec_knobs().stages;
   if (want >= sets && want < nst) nst = want;
   nst = nst / sets * sets;   // a stage is always consumed by the same set
   if (nst < sets) return false;
@@ -510,12 +521,10 @@ static bool dec_carve(const DecPlan &plan, int M, int rot_bytes, int sets, DecSm
 template <typename T, int SETS>
 static int max_resident_clusters(int c, int smem_bytes, int sms) {
   if (c == 1) return sms;
-  thread_local int cached_smem[4] = {0, 0, 0, 0}, cached_val[4] = {0, 0, 0, 0};
   int slot = 0;
   while ((1 << slot) < c) ++slot;
-  if (cached_smem[slot] == smem_bytes && cached_val[slot] > 0) return cached_val[slot];
   auto kern = decode_kernel<T, SETS>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmemLimit) != cudaSuccess) { (void)cudaGetLastError(); return 0; }   // never lowered: cached plans keep launching
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((sms / c) * c);
   cfg.blockDim = dim3(32 * (4 * SETS + 2));
@@ -529,9 +538,7 @@ static int max_resident_clusters(int c, int smem_bytes, int sms) {
   cfg.numAttrs = 1;
   int n = 0;
   if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
-  cached_smem[slot] = smem_bytes;
-  cached_val[slot] = n;
-  return n;
+  return n;   // (the caller caches the whole plan per shape, M and device)
 }
 
 // The launch plan: cluster size c (K slices), block ranges per partition, shared-memory carve-up.  Pure host logic --
@@ -586,20 +593,48 @@ int decode_debug_plan(const Layout &L, int64_t M, int sets, int sms, const int32
   return PARO_OK;
 }
 
+struct DecCached { bool found; DecPlan plan; DecSmem smem; };
+
 template <typename T, int SETS>
 static int launch_decode(DecParams &p, const Layout &L, int sms, cudaStream_t stream) {
   auto kern = decode_kernel<T, SETS>;
-  DecPlan best = {};
-  DecSmem best_s = {};
-  const bool found = dec_choose_plan(L, p.M, p.rot_bytes, SETS, sms, !dec_env_int("PARO_NO_CLUSTER", 0), dec_env_int("PARO_DECODE_C", 0),
-                                     [&](int c, int smem) { return max_resident_clusters<T, SETS>(c, smem, sms); }, best, best_s);
-  const long best_cost = found ? 0 : -1;
-  if (best_cost < 0) { set_error("decode: no launch configuration fits (in_features=%d, M=%d)", L.K, p.M); return PARO_EUNSUPPORTED; }
-  if (dec_env_int("PARO_DECODE_VERBOSE", 0))
+  const DecKnobs &kn = dec_knobs();
+  // the plan (cluster size, block ranges, shared-memory carve-up) depends on the shape, M and the device only: searched once
+  // (the search asks the occupancy API and sets the function attribute), then looked up -- an eager launch is a map lookup
+  struct Key {
+    int K, N, krot, n_parts, M, dev, parts[PARO_MAX_PARTS];
+    bool operator<(const Key &o) const { return memcmp(this, &o, sizeof(Key)) < 0; }
+  };
+  static std::mutex mu;
+  static std::map<Key, DecCached> cache;
+  Key key;
+  memset(&key, 0, sizeof(key));
+  key.K = L.K; key.N = L.N; key.krot = L.krot; key.n_parts = L.n_parts; key.M = p.M;
+  if (cudaGetDevice(&key.dev) != cudaSuccess) key.dev = 0;
+  for (int i = 0; i < L.n_parts; ++i) key.parts[i] = L.part_col_begin[i + 1] - L.part_col_begin[i];
+  DecCached c;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+      DecCached fresh = {};
+      fresh.found = dec_choose_plan(L, p.M, p.rot_bytes, SETS, sms, !kn.no_cluster, kn.force_c,
+                                    [&](int cc, int smem) { return max_resident_clusters<T, SETS>(cc, smem, sms); }, fresh.plan, fresh.smem);
+      if (fresh.found && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmemLimit) != cudaSuccess) {
+        (void)cudaGetLastError();
+        fresh.found = false;
+      }
+      it = cache.emplace(key, fresh).first;
+    }
+    c = it->second;
+  }
+  if (!c.found) { set_error("decode: no launch configuration fits (in_features=%d, M=%d)", L.K, p.M); return PARO_EUNSUPPORTED; }
+  const DecPlan &best = c.plan;
+  const DecSmem &best_s = c.smem;
+  if (kn.verbose)
     fprintf(stderr, "[paro decode] K=%d N=%d M=%d: cluster %d x %d ranges (grid %d), blocks/CTA <= %d, groups/CTA <= %d, %d stages, smem %d\n",
             L.K, L.N, p.M, best.c, best.ranges, best.grid, best.nj_max, best.ng_max, best_s.nstages, best_s.total);
 
-  PARO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, best_s.total));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(best.grid);
   cfg.blockDim = dim3(32 * (4 * SETS + 2));
@@ -614,7 +649,7 @@ static int launch_decode(DecParams &p, const Layout &L, int sms, cudaStream_t st
     attr[na].val.clusterDim.z = 1;
     ++na;
   }
-  if (!dec_env_int("PARO_NO_PDL", 0)) {
+  if (!kn.no_pdl) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
@@ -635,16 +670,18 @@ bool decode_supported(const Layout &L, int64_t M) { return M >= 1 && M <= 16 && 
 
 int decode_forward(const paro_linear_shape &s, const Layout &L, const void *packed, const void *x, int64_t M,
                    const void *bias, void *y, cudaStream_t stream) {
-  int dev = 0, sms = 0;
+  int dev = 0;
   PARO_CUDA_OK(cudaGetDevice(&dev));
-  PARO_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  static thread_local int sms_of[64] = {};   // SM count per device, asked once
+  if (!sms_of[dev & 63]) PARO_CUDA_OK(cudaDeviceGetAttribute(&sms_of[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+  const int sms = sms_of[dev & 63];
   DecParams p = {};
   p.packed = static_cast<const uint8_t *>(packed);
   p.x = x; p.y = y; p.bias = bias;
   p.M = static_cast<int>(M); p.K = L.K; p.N = L.N;
   p.n_parts = L.n_parts; p.groups = L.groups; p.krot = L.krot;
   p.rot_bytes = dec_rot_bytes(M);
-  p.trace = dec_env_int("PARO_DECODE_TRACE", 0);
+  p.trace = dec_knobs().trace;
   for (int i = 0; i <= PARO_MAX_PARTS; ++i) {
     p.part_col_begin[i] = L.part_col_begin[i];
     p.part_block_begin[i] = L.part_block_begin[i];
@@ -652,7 +689,7 @@ int decode_forward(const paro_linear_shape &s, const Layout &L, const void *pack
   p.meta_group_bytes = L.meta_group_bytes;
   p.meta_off = static_cast<long long>(L.meta_off);
   p.rec_off = static_cast<long long>(L.rec_off);
-  const int sets = dec_env_int("PARO_DECODE_SETS", 5);   // 5 sets x 4 dequant warps measured best (tools/microbench.py); 4..7 selectable
+  const int sets = dec_knobs().sets;   // 5 sets x 4 dequant warps measured best (tools/microbench.py); 4..7 selectable
   const bool bf16 = s.dtype == PARO_BF16;
   switch (sets) {
     case 4: return bf16 ? launch_decode<__nv_bfloat16, 4>(p, L, sms, stream) : launch_decode<__half, 4>(p, L, sms, stream);

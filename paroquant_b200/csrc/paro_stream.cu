@@ -57,7 +57,7 @@ constexpr uint32_t kStmDCol0 = 64 * kStmABufs;   // 448; D buffers take the last
 constexpr int kStmN = 16;                        // MMA N (M_mma = 128 needs N % 16 == 0)
 constexpr int kStmSmemLimit = 227 * 1024;
 constexpr int kStmStage = kBlockBytes;
-constexpr int kStmBarBytes = 16 * kStmMaxStages + 256;
+constexpr int kStmBarBytes = 16 * kStmMaxStages + 320;   // barriers (224 bytes after the ring's) + 16 rstd floats
 constexpr int kStmMiscBytes = 4096;              // epilogue scratch: per warp, 64 segments x {block, global block, contributors, my slot | reducer}
 
 constexpr int kStmTraceSlots = 12;
@@ -282,6 +282,35 @@ template <typename T> __device__ __forceinline__ uint32_t norm2(uint32_t h2, flo
   return pack2<T>(__hmul2(Traits<T>::from_floats(h.x * rstd, h.y * rstd), unpack2<T>(w2)));
 }
 
+// rstd[m] = rsqrt(mean(h^2) + eps) of every row from the producing step's per-(block, warp) partial sums, in a fixed order:
+// lane-strided serial sums, then a butterfly.  ONE warp per CTA polls the words (every consumer CTA needs the same 1 KB: all
+// warps of all CTAs polling it made those L2 lines a hot spot) and leaves the result in shared memory.
+__device__ __forceinline__ void stm_rstd(const StepDesc &S, int M, int lane, uint32_t tag, uint32_t rstd_smem) {
+  const int nb = S.stats_in_blocks;
+  for (int m = 0; m < M; ++m) {
+    float s = 0.f;
+    for (int b0 = lane; b0 < nb; b0 += 128) {   // four words in flight per lane (o / down: 4 x 32 blocks = 128 words)
+      uint2 e[4];
+      bool ok;
+      do {
+        ok = true;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (b0 + 32 * u < nb) {
+            e[u] = ld_relaxed_v2(S.stats_in + (b0 + 32 * u) * M + m);
+            ok = ok && e[u].y == tag;
+          }
+      } while (!ok);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (b0 + 32 * u < nb) s += __uint_as_float(e[u].x);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    if (lane == 0) sts_f32(rstd_smem + 4 * m, rsqrtf(s / static_cast<float>(S.K) + S.eps));
+  }
+}
+
 // 4 consecutive {T bits, tag} words -> two packed T2 words; false if any tag is stale
 __device__ __forceinline__ bool ll_unpack4(uint4 a, uint4 b, uint32_t tag, uint2 &out) {
   out.x = (a.x & 0xFFFFu) | (a.z << 16);
@@ -292,9 +321,11 @@ __device__ __forceinline__ bool ll_unpack4(uint4 a, uint4 b, uint32_t tag, uint2
 // this lane's 4 channels of group gk for rows m0 .. m0 + ROWS - 1, after the step's x op.  When x comes from an earlier
 // step of this launch it is read as {value, tag} words and re-read until every tag is this launch's.
 template <typename T, int ROWS>
-__device__ __forceinline__ void stm_load_x(const StepDesc &S, int M, int gk, int lane, uint2 (&raw)[ROWS], int m0, uint32_t tag) {
+__device__ __forceinline__ void stm_load_x(const StepDesc &S, int M, int gk, int lane, uint2 (&raw)[ROWS], int m0, uint32_t tag, uint32_t rstd_smem) {
   const int col = gk * kGroup + 4 * lane;
   const bool silu = S.x_op == PARO_XOP_SILU_MUL;
+  uint2 nw = make_uint2(0u, 0u);   // RMSNorm weights: fetched before x is waited for (x arrives last)
+  if (S.x_op == PARO_XOP_RMSNORM) nw = *reinterpret_cast<const uint2 *>(static_cast<const T *>(S.norm_w) + col);
   uint2 up[ROWS];
   if (S.x_ll) {
     bool ok;
@@ -313,6 +344,7 @@ __device__ __forceinline__ void stm_load_x(const StepDesc &S, int M, int gk, int
           }
         }
       }
+      if (!ok) __nanosleep(64);   // every CTA of a K slice polls the same words: do not hammer their L2 lines
     } while (!ok);
   } else {
     const T *xg = static_cast<const T *>(S.x) + col;
@@ -335,32 +367,11 @@ __device__ __forceinline__ void stm_load_x(const StepDesc &S, int M, int gk, int
       }
     }
   } else if (S.x_op == PARO_XOP_RMSNORM) {
-    const uint2 w = *reinterpret_cast<const uint2 *>(static_cast<const T *>(S.norm_w) + col);
-    const int nb = S.stats_in_blocks;
+    const uint2 w = nw;
 #pragma unroll
     for (int m = 0; m < ROWS; ++m) {
       if (m0 + m < M) {   // warp-uniform
-        // sum of the per-block partial sums of h^2 in a fixed order: lane-strided serial sums, then a butterfly
-        float s = 0.f;
-        for (int b0 = lane; b0 < nb; b0 += 128) {   // four words in flight per lane (o / down: 4 x 32 blocks = 128 words)
-          uint2 e[4];
-          bool ok;
-          do {
-            ok = true;
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (b0 + 32 * u < nb) {
-                e[u] = ld_relaxed_v2(S.stats_in + (b0 + 32 * u) * M + m0 + m);
-                ok = ok && e[u].y == tag;
-              }
-          } while (!ok);
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (b0 + 32 * u < nb) s += __uint_as_float(e[u].x);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-        const float rstd = rsqrtf(s / static_cast<float>(S.K) + S.eps);
+        const float rstd = lds_f32(rstd_smem + 4 * (m0 + m));   // one warp per CTA formed it (stm_rstd)
         raw[m].x = norm2<T>(raw[m].x, rstd, w.x);
         raw[m].y = norm2<T>(raw[m].y, rstd, w.y);
       }
@@ -389,9 +400,9 @@ __device__ __forceinline__ void stm_write_b_rows(uint32_t xb_group, uint32_t rot
 
 template <typename T, int ROWS>
 __device__ __forceinline__ void stm_rotate_task(const StepDesc &S, int M, int NR, const RotMeta &rm, int gk, int m0, int lane, uint32_t rot,
-                                                uint32_t xb_group, uint32_t tag) {
+                                                uint32_t xb_group, uint32_t tag, uint32_t rstd_smem) {
   uint2 raw[ROWS];
-  stm_load_x<T, ROWS>(S, M, gk, lane, raw, m0, tag);
+  stm_load_x<T, ROWS>(S, M, gk, lane, raw, m0, tag, rstd_smem);
   scale_and_stage<T, ROWS>(rot, lane, raw, rm.csw);
   __syncwarp();
   if (S.krot == 8) {
@@ -421,11 +432,11 @@ __device__ __forceinline__ void stm_rotate_task(const StepDesc &S, int M, int NR
 // tasks t = wi, wi + nwarps, ... of ng * nq (nq row blocks per group); the first task's metadata was fetched before the waits
 template <typename T, int ROWS>
 __device__ __forceinline__ void stm_prologue(const StepDesc &S, int M, int NR, RotMeta &rm, const StepGeom &g, int ntasks, int nq, int wi,
-                                             int nwarps, int lane, uint32_t rot, uint32_t xb, uint32_t tag) {
+                                             int nwarps, int lane, uint32_t rot, uint32_t xb, uint32_t tag, uint32_t rstd_smem) {
   for (int t = wi; t < ntasks; t += nwarps) {
     const int gi = t / nq, rq = t - gi * nq;
     if (t != wi) stm_fetch_meta(S, g.part, g.g_begin + gi, lane, rm);
-    stm_rotate_task<T, ROWS>(S, M, NR, rm, g.g_begin + gi, rq * ROWS, lane, rot, xb + gi * (NR * 256), tag);
+    stm_rotate_task<T, ROWS>(S, M, NR, rm, g.g_begin + gi, rq * ROWS, lane, rot, xb + gi * (NR * 256), tag, rstd_smem);
   }
 }
 
@@ -626,6 +637,10 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 6), 1) stream_kernel(const __
       // if something is missing (`wait` = false: one look).
       auto sum_block = [&](int gb, int total, unsigned long long bit, float (&acc)[MB]) -> bool {
         const bool pushed = (pushed_mask & bit) != 0ull;
+        if (S.epi_op == PARO_EPI_ADD_RESIDUAL) {   // warm the residual lines this block's finish will read (they sit in L2)
+          const int n = S.part_col_begin[g.part] + (gb - S.part_block_begin[g.part]) * kBlockN + L128;
+          if (n < n_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const T *>(S.res_in) + n));
+        }
         if (!pushed) {
 #pragma unroll
           for (int m = 0; m < MB; ++m) acc[m] = 0.f;
@@ -767,6 +782,7 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 6), 1) stream_kernel(const __
     const int nq = M > 4 ? (M + 3) >> 2 : 1;   // rotation tasks: row blocks of 4 for M > 4
     uint32_t rr_base = 0;                      // global round index (over all steps) of this step's first round
     uint32_t tag = 0;
+    const uint32_t rstd_smem = bars + 16 * kStmMaxStages + 224;   // 16 floats behind the barriers
     // my next round: rr; ring stage / parity, A buffer / use derived incrementally
     uint32_t rr = e;
     int st = e, par = 0, a = e, ause = 0;
@@ -794,14 +810,19 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 6), 1) stream_kernel(const __
       // the previous step's MMAs no longer read the B operand (every worker warp waits, so each consumes the phases in order)
       if (i > 0) mbar_wait(bar_stepdone, (i - 1) & 1);
       if (mine) {
+        if (S.x_op == PARO_XOP_RMSNORM) {
+          const int nrot = ntasks < p.rot_warps ? ntasks : p.rot_warps;   // the warps that rotate in this step (warp 0 is one)
+          if (wi == 0) stm_rstd(S, M, lane, tag, rstd_smem);
+          named_bar_sync(3, 32 * nrot);
+        }
         if (wi == 0) STM_TRACE(i, 2);
         if constexpr (MB == 1) {
-          stm_prologue<T, 1>(S, M, NR, rm, g, ntasks, nq, wi, p.rot_warps, lane, rot, xb, tag);
+          stm_prologue<T, 1>(S, M, NR, rm, g, ntasks, nq, wi, p.rot_warps, lane, rot, xb, tag, rstd_smem);
         } else if constexpr (MB == 4) {
-          if (M == 2) stm_prologue<T, 2>(S, M, NR, rm, g, ntasks, nq, wi, p.rot_warps, lane, rot, xb, tag);
-          else stm_prologue<T, 4>(S, M, NR, rm, g, ntasks, nq, wi, p.rot_warps, lane, rot, xb, tag);
+          if (M == 2) stm_prologue<T, 2>(S, M, NR, rm, g, ntasks, nq, wi, p.rot_warps, lane, rot, xb, tag, rstd_smem);
+          else stm_prologue<T, 4>(S, M, NR, rm, g, ntasks, nq, wi, p.rot_warps, lane, rot, xb, tag, rstd_smem);
         } else {
-          stm_prologue<T, 4>(S, M, NR, rm, g, ntasks, nq, wi, p.rot_warps, lane, rot, xb, tag);
+          stm_prologue<T, 4>(S, M, NR, rm, g, ntasks, nq, wi, p.rot_warps, lane, rot, xb, tag, rstd_smem);
         }
         fence_proxy_async_smem();  // B rows were written through the generic proxy, tcgen05.mma reads them through the async proxy
       }

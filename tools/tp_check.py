@@ -35,7 +35,7 @@ def err(a, b):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--m", type=int, default=1)
+    ap.add_argument("--batch", dest="m", type=int, default=1)
     ap.add_argument("--layers", type=int, default=6)
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--small", action="store_true", help="hidden 1024 / inter 2048 (quick parity run)")
