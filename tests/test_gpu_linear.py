@@ -255,3 +255,19 @@ def test_prefill_4096_vs_oracle_samples(PK, oracle, name, K, parts):
         got = y[np.ix_(rows, cols)]
         assert oracle.rel_err(got, ref) < TOL, (name, p)
         n0 += n
+
+
+def test_linear_op_is_opaque_under_torch_compile(PK):
+    """vLLM traces `ParoQuantLinearMethod.apply` with fullgraph=True and a symbolic batch dimension: the call must be ONE opaque
+    op (no ctypes, no Python branch on the row count in `ParoLinearKernel.__call__`), for decode and prefill sizes alike."""
+    L = make_synthetic_layer(1024, [256, 128], seed=77, bias=True)
+    k = PK.from_buffers(L.to("cuda"), torch.bfloat16, check_pairs=False)   # default max_m = 16: prefill sizes must still work
+    bias = L.bias.to("cuda")                                                # fp16 checkpoint bias meets bf16 activations
+
+    def f(x):
+        return k(x * 1.0, bias) + 0.0
+
+    cf = torch.compile(f, fullgraph=True, dynamic=True)
+    for M in (1, 7, 48, 300):
+        x = make_synthetic_activations(M, 1024, seed=M, device="cuda")
+        assert torch.equal(cf(x), f(x))
