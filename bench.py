@@ -45,20 +45,24 @@ SHAPES = {  # name: (K, part_sizes, kind)
 }
 
 
-def traffic_from_profile():
-    """DRAM bytes (read + write) of ONE launch of the dominant kernel, from the committed `ncu --set full` summary
-    (profiles/r01_decode_gate_up_m1_ncu.txt: the gate_up launch, 61.29 MB algorithmic).  None if the file is absent."""
-    f = ROOT / "profiles" / "r01_decode_gate_up_m1_ncu.txt"
-    if not f.exists():
+def traffic_from_profile(kernel="decode"):
+    """DRAM bytes (read + write) of ONE launch of the dominant kernel, from the committed `ncu --set full` summaries:
+    decode_kernel on gate_up (61.29 MB algorithmic) or one stream_kernel chain launch (one block: 114.5 MB algorithmic)."""
+    f, what, alg = {
+        "decode": ("r02_decode_gate_up_m1_ncu.txt", "decode_kernel, gate_up 4096->28672 M=1", algorithmic_bytes(4096, [14336, 14336], 1)),
+        "chain": ("r02_chain_m1_ncu.txt", "stream_kernel, one chain launch (o, gate_up, down, qkv) M=1",
+                  sum(algorithmic_bytes(K, p, 1) for K, p, _ in SHAPES.values())),
+    }[kernel]
+    path = ROOT / "profiles" / f
+    if not path.exists():
         return None
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     tot = 0.0
-    for ln in f.read_text().splitlines():
+    for ln in path.read_text().splitlines():
         t = ln.split()
         if len(t) >= 3 and t[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and t[2] in unit:
             tot += float(t[1].replace(",", "")) * unit[t[2]]
-    return {"bytes_per_launch": tot, "launch": "gate_up 4096->28672 M=1", "algorithmic_bytes": algorithmic_bytes(4096, [14336, 14336], 1),
-            "source": "profiles/r01_decode_gate_up_m1_ncu.txt"} if tot else None
+    return {"bytes_per_launch": tot, "launch": what, "algorithmic_bytes": alg, "source": f"profiles/{f}"} if tot else None
 
 
 def measured_peaks():
@@ -149,6 +153,7 @@ class DecodeModel:
             self.qkv0 = torch.empty(M, (HIDDEN + 2 * KV) // world, dtype=dt, device=dev)
             res = make_synthetic_activations(M, HIDDEN, seed=78, device=dev, dtype=dt)
             w = torch.ones(HIDDEN, dtype=dt, device=dev)
+            self.res0, self.norm_w = res, w
             self.chains, self.copies = [], []
             qkv = self.qkv0
             for li, lk in enumerate(self.layers):
@@ -179,6 +184,25 @@ class DecodeModel:
             n += _cabi.last_launch_count()
         self.launches = n
         return self.final
+
+    def token_linear_with_neighbours(self):
+        """token_linear + what vLLM launches between the linears (fused_add_rms_norm x2, silu_and_mul per block), as plain torch
+        kernels: the same work a chain launch does -- the like-for-like partner of `token_chain`."""
+        import torch.nn.functional as F
+        from paroquant_b200 import _cabi
+        n, x, res = 0, self.x0, self.res0
+        w = self.norm_w
+        for lk in self.layers:
+            qkv = lk["qkv"](x); n += _cabi.last_launch_count()
+            o = lk["o"](qkv[:, :HIDDEN]); n += _cabi.last_launch_count()
+            res = o + res
+            gu = lk["gate_up"](F.rms_norm(res, (HIDDEN,), w, 1e-5)); n += _cabi.last_launch_count()
+            act = F.silu(gu[:, :INTER]) * gu[:, INTER:]
+            d = lk["down"](act); n += _cabi.last_launch_count()
+            res = d + res
+            x = F.rms_norm(res, (HIDDEN,), w, 1e-5)
+        self.launches = n
+        return res
 
     def token_linear(self):
         from paroquant_b200 import _cabi
@@ -316,6 +340,11 @@ def run_ours(args):
                       "api": "ParoLinearKernel.__call__ -> torch.ops.paro.linear (the call ParoQuantLinearMethod.apply makes), one launch per "
                              "linear, activations chained by slices, vLLM's norm / activation kernels not run"}
 
+    if per_linear is not None:
+        ms_n, _, _ = timed_graph(torch, model.token_linear_with_neighbours, max(args.steps // 2, 5), 3, barrier, use_graph)
+        per_linear["with_neighbour_kernels"] = {"tokens_per_s": M * 1e3 / ms_n, "ms_per_step": ms_n,
+                                                 "what": "the same 128 launches + torch's rms_norm / silu*mul / residual-add kernels between them: "
+                                                         "the work one chain launch per block does"}
     chain_res = {"tokens_per_s": M * 1e3 / ms, "ms_per_step": ms, "launches_per_step": chain_launches, "e2e_tokens_per_s": M * 1e3 / ms_e2e,
                  "api": "paroquant_b200.chain.ParoChain (paro_chain_forward): norms, SiLU*up and residual adds folded in"}
     headline = "chain"
@@ -367,7 +396,7 @@ def run_ours(args):
             "gpu_launches": launches_per_step * args.steps,
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": traffic_from_profile(), "peak_source": src, "kernel": "paro::stream_kernel", "launches_per_step": launches_per_step,
+                         "traffic": traffic_from_profile("chain"), "peak_source": src, "kernel": "paro::stream_kernel", "launches_per_step": launches_per_step,
                          "algorithmic_bytes_per_step": step_bytes, "avg_launch_us": ms * 1e3 / max(launches_per_step, 1)},
         }
         line["config"]["headline_path"] = headline
@@ -381,6 +410,7 @@ def run_ours(args):
             line["config"]["path"] = "128 launches, one per (merged) linear, through torch.ops.paro.linear; activations chained by slices"
             line["e2e"]["api"] = "ParoLinearKernel.__call__ -> torch.ops.paro.linear"
             line["roofline"]["kernel"] = "paro::decode_kernel"
+            line["roofline"]["traffic"] = traffic_from_profile("decode")
         if world == 1 and not args.no_ref_gpu:
             line["vs_reference_gpu"] = reference_gpu_section(M, line["value"], per_linear)
         if world == 1 and not args.no_prefill:

@@ -82,3 +82,48 @@ def test_null_and_bad_arguments_return_codes():
     assert rc == 1 and b"Float, Half, and BFloat16" in lib.paro_last_error()
     rc = lib.paro_rotate(p, p, p, p, 1, None, 0, 0, 128, 8, 128, 2, None)   # empty input: no launch, success
     assert rc == 0 and lib.paro_last_launch_count() == 0
+
+
+def _chain(steps):
+    arr = (_cabi.ParoChainStep * len(steps))()
+    keep = []
+    for c, kw in zip(arr, steps):
+        shape = kw.pop("shape")
+        keep.append(shape)
+        c.shape = ctypes.pointer(shape)
+        c.packed = 0x10000 if kw.pop("packed", True) else None      # never dereferenced by the host-side checks
+        for k, v in kw.items():
+            setattr(c, k, v)
+    return arr, keep
+
+
+def test_chain_host_checks_and_sizes():
+    """paro_chain_workspace_bytes / paro_tp_slot_bytes and the argument checks of a chain, host side only."""
+    lib = _cabi.lib()
+    o = _cabi.make_shape(4096, [4096], 128, 8, torch.bfloat16)
+    gu = _cabi.make_shape(4096, [14336, 14336], 128, 8, torch.bfloat16)
+    down = _cabi.make_shape(14336, [4096], 128, 8, torch.bfloat16)
+    arr, keep = _chain([dict(shape=o, x=0x20000, epilogue=_cabi.EPI_ADD_RESIDUAL, residual_in=0x30000, residual_out=0x40000),
+                        dict(shape=gu, x_op=_cabi.XOP_RMSNORM, norm_weight=0x50000, y=0x60000),
+                        dict(shape=down, x_op=_cabi.XOP_SILU_MUL, y=0x70000)])
+    one = lib.paro_chain_workspace_bytes(arr, 1, 1)
+    three = lib.paro_chain_workspace_bytes(arr, 3, 1)
+    assert 256 < one < three < 64 << 20
+    assert lib.paro_chain_workspace_bytes(arr, 3, 16) > three          # slots and published words grow with the rows
+    assert lib.paro_chain_workspace_bytes(arr, 3, 17) == 0 and b"M <= 16" in lib.paro_last_error()
+    assert lib.paro_chain_workspace_bytes(arr, 7, 1) == 0 and b"steps" in lib.paro_last_error()
+    bad, keep2 = _chain([dict(shape=o, x=0x20000, epilogue=_cabi.EPI_ADD_RESIDUAL, residual_in=0x30000, residual_out=0x30000)])
+    assert lib.paro_chain_workspace_bytes(bad, 1, 1) == 0 and b"alias" in lib.paro_last_error()
+    bad, keep3 = _chain([dict(shape=o, x=0x20000, x_op=7, y=0x30000)])
+    assert lib.paro_chain_workspace_bytes(bad, 1, 1) == 0 and b"x_op" in lib.paro_last_error()
+    # tensor parallel: 2 halves (launch parity) x blocks x ranks x rows x 128 columns x 8-byte {value, tag} words
+    assert lib.paro_tp_slot_bytes(ctypes.byref(o), 1, 8) == 2 * 32 * 8 * 1 * 128 * 8
+    assert lib.paro_tp_slot_bytes(ctypes.byref(o), 4, 2) == 2 * 32 * 2 * 4 * 128 * 8
+    assert lib.paro_tp_slot_bytes(ctypes.byref(o), 1, 9) == 0
+    info = _cabi.ParoTpInfo()
+    info.world, info.rank = 2, 0
+    info.peer_slots[0] = 0x100000                                     # rank 1's buffer missing
+    tp, keep4 = _chain([dict(shape=o, x=0x20000, y=0x30000, tp=ctypes.pointer(info))])
+    assert lib.paro_chain_workspace_bytes(tp, 1, 1) == 0 and b"peer_slots[1]" in lib.paro_last_error()
+    info.rank = 2
+    assert lib.paro_chain_workspace_bytes(tp, 1, 1) == 0 and b"rank < world" in lib.paro_last_error()

@@ -62,3 +62,64 @@ def test_row_and_column_parallel_world2(tmp_path, oracle):
     assert np.allclose(got["row"].numpy(), acc, rtol=1e-12, atol=1e-12)
     ref = oracle.linear(x, d, "bfloat16")
     assert np.array_equal(got["col"].numpy(), ref)
+
+
+def _chain_worker(rank, world, port, out):
+    """The tensor-parallel decoder tail as bench.py --gpus N runs it, with the oracle standing in for the kernels: o / down
+    row-sharded, gate_up / qkv column-sharded; a row-parallel step exchanges fp32 block sums and every rank adds them IN RANK
+    ORDER before the one rounding to T (what paro_stream.cu does with its peer buffers) -- here all_gather + a fixed-order sum."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as O
+
+    hid, inter, M, dt = 256, 512, 3, "bfloat16"
+    full = {"o": make_synthetic_layer(hid, [hid], seed=21), "gate_up": make_synthetic_layer(hid, [inter, inter], seed=22),
+            "down": make_synthetic_layer(inter, [hid], seed=23), "qkv": make_synthetic_layer(hid, [hid, 64, 64], seed=24)}
+    attn = make_synthetic_activations(M, hid, seed=5, dtype=torch.float32).numpy()
+    resid = make_synthetic_activations(M, hid, seed=6, dtype=torch.float32).numpy()
+    w = np.ones(hid, np.float32)
+
+    def row_parallel(name, x_shard):
+        d = shard_rows(full[name], rank, world).numpy_dict()
+        xr = O.c_rotate(x_shard, d["pairs"][0], d["theta"][0], d["channel_scales"][0], 128, dt)
+        W = O.c_dequant(d["qweight"], d["qzeros"], d["scales"], 128, dt)
+        part = torch.from_numpy((xr.astype(np.float64) @ W.astype(np.float64)).astype(np.float32))   # this rank's fp32 block sums
+        parts = [torch.empty_like(part) for _ in range(world)]
+        dist.all_gather(parts, part)                                   # stands in for the stores into every rank's peer buffer
+        acc = np.zeros_like(part.numpy())
+        for p in parts:                                                # rank order, fp32
+            acc = acc + p.numpy()
+        return O.round_to(acc, dt)
+
+    ks = hid // world
+    h1 = O.add_residual(row_parallel("o", attn[:, rank * ks:(rank + 1) * ks]), resid, dt)
+    act = O.linear(O.rms_norm(h1, w, 1e-5, dt), shard_columns(full["gate_up"], rank, world).numpy_dict(), dt)   # [gate shard | up shard]
+    h2 = O.add_residual(row_parallel("down", O.silu_and_mul(act, dt)), h1, dt)
+    qkv = O.linear(O.rms_norm(h2, w, 1e-5, dt), shard_columns(full["qkv"], rank, world).numpy_dict(), dt)
+    t = torch.from_numpy(np.ascontiguousarray(h2))
+    allh = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(allh, t)
+    if rank == 0:
+        torch.save({"h2": allh, "qkv0": torch.from_numpy(qkv)}, out)
+    dist.destroy_process_group()
+
+
+def test_tensor_parallel_decoder_tail_world2(tmp_path, oracle):
+    out = str(tmp_path / "tail.pt")
+    mp.spawn(_chain_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    assert torch.equal(got["h2"][0], got["h2"][1]), "the residual stream must be bit-identical on every rank"
+    O = oracle
+    hid, inter, M, dt = 256, 512, 3, "bfloat16"
+    full = {"o": make_synthetic_layer(hid, [hid], seed=21), "gate_up": make_synthetic_layer(hid, [inter, inter], seed=22),
+            "down": make_synthetic_layer(inter, [hid], seed=23), "qkv": make_synthetic_layer(hid, [hid, 64, 64], seed=24)}
+    attn = make_synthetic_activations(M, hid, seed=5, dtype=torch.float32).numpy()
+    resid = make_synthetic_activations(M, hid, seed=6, dtype=torch.float32).numpy()
+    w = np.ones(hid, np.float32)
+    d = {n: L.numpy_dict() for n, L in full.items()}
+    h1 = O.add_residual(O.linear(attn, d["o"], dt), resid, dt)
+    h2 = O.add_residual(O.linear(O.silu_and_mul(O.linear(O.rms_norm(h1, w, 1e-5, dt), d["gate_up"], dt), dt), d["down"], dt), h1, dt)
+    assert O.rel_err(got["h2"][0].numpy(), h2) < 2e-3      # another split of K: rounding-level differences, carried through two stages
+    qkv = O.linear(O.rms_norm(h2, w, 1e-5, dt), d["qkv"], dt)
+    cols = np.concatenate([np.arange(0, 128), np.arange(256, 288), np.arange(320, 352)])   # rank 0's share of q, k, v
+    assert O.rel_err(got["qkv0"].numpy(), qkv[:, cols]) < 4e-3
