@@ -217,11 +217,33 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const GemmPara
 }
 
 // ------------------------------------------------------------------ host side
-static int pick_nt(int64_t M) { return M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256; }
+// Tokens per output tile.  The tensor pipe needs ~135 cycles per M128 x N256 x K16 MMA (8 per round), a dequant set ~520
+// cycles per round: N = 256 tiles keep the tensor pipe busy, but a small batch x few column blocks gives fewer tiles than SMs
+// (256 tokens x 4096 columns = 32 tiles) and is better cut finer -- pick the size with the shortest critical path
+// (waves x (rounds x max(dequant, MMA) + per-tile prologue / read-back)).
+static int pick_nt(int64_t M, const Layout &L) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+  }
+  // from the largest tile the batch allows downwards: a finer tile must be CLEARLY better on paper (>= 25 %) -- finer tiles
+  // re-read the weights more often and sit at the dequant limit, which the model prices optimistically
+  int best = 0;
+  double best_t = 0;
+  for (int nt = 256; nt >= 32; nt /= 2) {
+    if (nt > 32 && M <= nt / 2) continue;   // never pad the batch more than 2x
+    const int64_t tiles = (M + nt - 1) / nt * L.blocks_total;
+    const int64_t waves = (tiles + sms - 1) / sms;
+    const double per_round = nt * (8.0 * 135.0 / 256.0) > 520.0 ? nt * (8.0 * 135.0 / 256.0) : 520.0;
+    const double t = static_cast<double>(waves) * (L.groups * per_round + 4000.0 + 16.0 * nt);
+    if (!best || t < 0.75 * best_t) { best = nt; best_t = t; }
+  }
+  return best;
+}
 
 size_t gemm_workspace_bytes(const Layout &L, int64_t max_m) {
-  const int NT = pick_nt(max_m);
-  const int64_t m_pad = (max_m + NT - 1) / NT * NT;
+  const int64_t m_pad = (max_m + 255) / 256 * 256;           // whatever tile size a later call picks
   return static_cast<size_t>(L.n_parts) * m_pad * L.K * 2;   // x_rot per partition, B-operand tile order
 }
 
@@ -251,7 +273,7 @@ int gemm_forward(const paro_linear_shape &s, const Layout &L, const void *packed
     set_error("workspace too small: have %zu, need %zu", workspace_bytes, gemm_workspace_bytes(L, M));
     return PARO_EWORKSPACE;
   }
-  const int NT = pick_nt(M);
+  const int NT = pick_nt(M, L);
   const int64_t m_pad = (M + NT - 1) / NT * NT;
   const uint8_t *pk = static_cast<const uint8_t *>(packed);
   uint8_t *xr_base = static_cast<uint8_t *>(workspace);

@@ -2,7 +2,7 @@
 `ParoQuantLinearMethod`) delegate to.  One C-ABI call per forward
 (include/paro_b200.h: paro_linear_forward), exposed to torch.compile / CUDA graphs as
 
-    paro::linear(Tensor x, Tensor packed, Tensor(a!) workspace, Tensor? bias, int[] meta) -> Tensor
+    paro::linear(Tensor x, Tensor packed, Tensor? workspace, Tensor? bias, int[] meta) -> Tensor
 
 meta = [in_features, group_size, krot, dtype_code, *part_sizes].
 """
@@ -14,7 +14,10 @@ from . import _cabi
 from .checkpoint import ParoLayerBuffers, validate_pairs
 
 torch.library.define(
-    "paro::linear", "(Tensor x, Tensor packed, Tensor(a!)? workspace, Tensor? bias, int[] meta) -> Tensor")
+    "paro::linear", "(Tensor x, Tensor packed, Tensor? workspace, Tensor? bias, int[] meta) -> Tensor")
+# `workspace` is scratch (plus the launch epoch, which only the kernels read): it is NOT declared as mutated -- a mutable optional
+# argument sends torch.compile through auto_functionalized, which Inductor (2.11) fails to lower for this op; launches are stream
+# ordered anyway, so nothing can observe the scratch between two calls
 
 _shape_cache: dict[tuple, _cabi.ParoLinearShape] = {}
 
@@ -28,11 +31,30 @@ def _shape_from_meta(meta) -> _cabi.ParoLinearShape:
     return s
 
 
+_bias_casts: dict[tuple, tuple] = {}
+
+
+def _bias_as(bias, dtype):
+    """Bias in the activation dtype; a checkpoint's fp16 bias meeting bf16 activations is cast ONCE (per bias tensor and version),
+    not per forward (the reference pays a cast kernel on every call)."""
+    if bias is None or (bias.dtype == dtype and bias.is_contiguous()):
+        return bias
+    key = (bias.data_ptr(), dtype)
+    hit = _bias_casts.get(key)
+    if hit is None or hit[0] != bias._version or hit[1].shape != bias.shape:
+        if len(_bias_casts) > 4096:
+            _bias_casts.clear()
+        hit = (bias._version, bias.to(dtype).contiguous())
+        _bias_casts[key] = hit
+    return hit[1]
+
+
 @torch.library.impl("paro::linear", "CUDA")
 def _linear_cuda(x, packed, workspace, bias, meta):
     # Everything that looks at sizes lives HERE, inside the opaque op: torch.compile / vLLM trace `__call__` with a symbolic
     # batch dimension and must see a branch-free call (no ctypes, no `m > max_m`).
     shape = _shape_from_meta(meta)
+    bias = _bias_as(bias, x.dtype)
     if workspace is None:
         m = x.numel() // shape.in_features
         workspace = shared_workspace(x.device, _cabi.workspace_bytes(shape, max(m, 1)))
@@ -84,7 +106,6 @@ class ParoLinearKernel:
         self.dtype = _cabi._CODE_DTYPE[shape.dtype]
         self.private_workspace = private_workspace
         self._private = _cabi.new_workspace(shape, max_m, packed.device) if private_workspace else None
-        self._bias_cache: tuple | None = None
         shared_workspace(packed.device, _cabi.workspace_bytes(shape, max_m))   # warm the shared scratch outside any capture
 
     @classmethod
@@ -111,23 +132,14 @@ class ParoLinearKernel:
         """The scratch the next launch will use (tools and benches that call the C-ABI directly)."""
         return self._private if self._private is not None else shared_workspace(self.packed.device, 0)
 
-    def _bias(self, bias: torch.Tensor | None) -> torch.Tensor | None:
-        """Bias in the activation dtype; a checkpoint's fp16 bias meeting bf16 activations is cast ONCE, not per forward."""
-        if bias is None or (bias.dtype == self.dtype and bias.is_contiguous()):
-            return bias
-        c = self._bias_cache
-        if c is None or c[0] is not bias or c[1] != bias._version:
-            self._bias_cache = c = (bias, bias._version, bias.to(self.dtype).contiguous())
-        return c[2]
-
     def __call__(self, x: torch.Tensor, bias: torch.Tensor | None = None) -> torch.Tensor:
-        return torch.ops.paro.linear(x, self.packed, self._private, self._bias(bias), self.meta)
+        return torch.ops.paro.linear(x, self.packed, self._private, bias, self.meta)   # nothing here looks at sizes or dtypes
 
     def forward_into(self, x: torch.Tensor, out: torch.Tensor, bias: torch.Tensor | None = None) -> torch.Tensor:
         """Same as __call__ but writes into a caller-owned [.., N] buffer (fixed addresses for CUDA graphs / chains)."""
         m = x.numel() // self.shape.in_features
         ws = self._private if self._private is not None else shared_workspace(x.device, _cabi.workspace_bytes(self.shape, max(m, 1)))
-        return _cabi.linear_forward(self.shape, self.packed, x, self._bias(bias), ws, out=out)
+        return _cabi.linear_forward(self.shape, self.packed, x, _bias_as(bias, self.dtype), ws, out=out)
 
     def dense_weight(self) -> torch.Tensor:
         """[K, N] dequantised operand T((q - z) * s) exactly as the kernels form it (tests)."""

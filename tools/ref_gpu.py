@@ -194,8 +194,36 @@ def bench(out: Path, ms: list[int]) -> None:
     out.write_text(json.dumps(res, indent=1))
 
 
+def rotbench(which: str) -> None:
+    """Standalone rotate op, ours vs the reference's kernel (separate processes: same op name): us and GB/s (read + write)."""
+    if which == "reference":
+        rotate = load_reference_rotate()
+    else:
+        import paroquant_b200.kernels.cuda  # noqa: F401
+        rotate = torch.ops.rotation.rotate
+    for K in (4096, 14336):
+        L = make_synthetic_layer(K, [64], seed=3, device="cuda")
+        for M in (1, 16, 256, 4096):
+            x = make_synthetic_activations(M, K, seed=4, device="cuda")
+            for _ in range(3):
+                rotate(x, L.pairs[0], L.theta[0], L.channel_scales[0])
+            torch.cuda.synchronize()
+            reps = 200 if M <= 256 else 30
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                rotate(x, L.pairs[0], L.theta[0], L.channel_scales[0])
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / reps
+            print(f"rotate[{which:9s}] K={K:5d} M={M:5d} {us:9.2f} us  {2 * M * K * 2 / us / 1e3:8.1f} GB/s", flush=True)
+
+
 if __name__ == "__main__":
     cmd = sys.argv[1]
+    if cmd == "rotbench":
+        rotbench(sys.argv[2])
+        sys.exit(0)
     if cmd == "golden":
         golden(Path(sys.argv[2]))
     elif cmd == "run":
