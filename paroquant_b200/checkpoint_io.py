@@ -99,6 +99,69 @@ def export_layer(state: dict, device="cuda") -> tuple[dict[str, torch.Tensor], i
     return buffers, bits, group, int(theta.shape[0])
 
 
+def export_moe(state: dict, device="cuda") -> tuple[dict[str, dict[str, torch.Tensor]], dict[str, torch.Tensor], int, int, int]:
+    """Optimiser state of one fused MoE expert block (reference ``convert.py:281-381``, ``_quantize_moe``) -> per-projection expert
+    stacks ``{gate_proj, up_proj, down_proj: {qweight [E, K, N/8], qzeros [E, K/G, N/8], scales [E, K/G, N]}}`` and the rotation
+    buffers ALL experts share (one rotation of x before gate / up, one of the activation before down), bits, group_size, krot.
+    ``gate_up_weight`` is [E, 2I, H] (gate rows first), ``down_weight`` [E, H, I]; quantiser scales / zero points are per
+    (expert row, group), flattened in that order."""
+    import paroquant_b200.kernels.cuda  # noqa: F401  registers the op
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("export_moe: the weight rotation is CUDA-only (no CPU fallback)")
+    bits = int(_first(state, "n_bits", "quantizer.n_bits"))
+    group = int(_first(state, "group_size", "quantizer.group_size"))
+    gate_up = state["gate_up_weight"].to(device=dev, dtype=torch.float32)
+    down = state["down_weight"].to(device=dev, dtype=torch.float32)
+    E, gu_out, gu_in = gate_up.shape
+    _, d_out, d_in = down.shape
+    if gu_in != d_out:
+        raise ValueError(f"Unexpected MoE shapes: gate_up={tuple(gate_up.shape)} down={tuple(down.shape)}")   # convert.py:293-294
+    rot, quant = {}, {}
+    for tag, w, n_in in (("gate_up", gate_up, gu_in), ("down", down, d_in)):
+        pairs = _stacked(state, f"{tag}_pairs_grouped").to(device=dev, dtype=torch.int16)
+        theta = _stacked(state, f"{tag}_angles_grouped").to(device=dev, dtype=torch.float32)
+        cs = state[f"{tag}_channel_scales"].to(device=dev, dtype=torch.float32).reshape(1, -1)
+        validate_pairs(pairs, group)
+        rotated = torch.ops.rotation.rotate(w.reshape(-1, n_in) * cs, pairs, theta, None, group)
+        quant[tag] = quantize_rotated(rotated, state[f"{tag}_quantizer.scale"].to(dev), state[f"{tag}_quantizer.zero_point_float"].to(dev),
+                                      bits=bits, group_size=group)
+        rot[f"{tag}_weight_theta"] = theta.to(torch.float16).cpu()
+        rot[f"{tag}_weight_pairs"] = pairs.cpu()
+        rot[f"{tag}_weight_channel_scales"] = (1.0 / cs).to(torch.float16).cpu()
+    return moe_expert_buffers(quant["gate_up"], quant["down"], E), rot, bits, group, int(rot["gate_up_weight_theta"].shape[0])
+
+
+def moe_expert_buffers(gate_up_q, down_q, num_experts: int) -> dict[str, dict[str, torch.Tensor]]:
+    """(q, scales, zeros) of the flattened expert rows -> AWQ buffers stacked per expert, gate rows / up rows split
+    (convert.py:339-366).  Plain integer work: runs anywhere."""
+    q, s, z = gate_up_q
+    gu_out = q.shape[0] // num_experts
+    half = gu_out // 2
+    q, s, z = (t.reshape(num_experts, gu_out, -1) for t in (q, s, z))
+    dq, ds, dz = (t.reshape(num_experts, down_q[0].shape[0] // num_experts, -1) for t in down_q)
+    out: dict[str, dict[str, torch.Tensor]] = {}
+    for proj, (qq, ss, zz) in (("gate_proj", (q[:, :half], s[:, :half], z[:, :half])), ("up_proj", (q[:, half:], s[:, half:], z[:, half:])),
+                               ("down_proj", (dq, ds, dz))):
+        per = [to_awq_buffers(qq[e], ss[e], zz[e]) for e in range(num_experts)]
+        out[proj] = {k: torch.stack([b[k] for b in per]) for k in ("qweight", "qzeros", "scales")}
+    return out
+
+
+def moe_state_entries(base_prefix: str, proj_buffers: dict, rotation_buffers: dict) -> dict[str, torch.Tensor]:
+    """Checkpoint names of one expert block (convert.py:384-406): ``<base>.<e>.<proj>.{qweight,qzeros,scales}`` per expert and
+    ``<base>.{gate_up,down}_weight_{theta,pairs,channel_scales}`` once."""
+    out = {}
+    E = proj_buffers["gate_proj"]["qweight"].shape[0]
+    for e in range(E):
+        for proj in ("gate_proj", "up_proj", "down_proj"):
+            for leaf in ("qweight", "qzeros", "scales"):
+                out[f"{base_prefix}.{e}.{proj}.{leaf}"] = proj_buffers[proj][leaf][e]
+    for name, t in rotation_buffers.items():
+        out[f"{base_prefix}.{name}"] = t
+    return out
+
+
 def save_paro_checkpoint(out_dir, tensors: dict[str, torch.Tensor], *, bits: int = 4, group_size: int = 128, krot: int = 8,
                          base_config: dict | None = None) -> Path:
     """Write `tensors` (full state-dict names, e.g. ``model.layers.0.self_attn.q_proj.qweight``) as ``model.safetensors``
@@ -119,6 +182,8 @@ class ParoCheckpoint:
     quant_config: dict
     layers: dict[str, ParoLayerBuffers]                      # quantised modules, one partition each
     dense: dict[str, torch.Tensor] = field(default_factory=dict)   # every other tensor, untouched
+    experts: dict[str, list[dict[str, ParoLayerBuffers]]] = field(default_factory=dict)
+    # MoE blocks: <base> -> per expert {"gate_up": merged gate | up, "down": ...}; all experts of a block carry the SAME rotation
 
     @property
     def quantized_modules(self) -> set[str]:
@@ -166,6 +231,37 @@ def load_paro_checkpoint(model_dir, *, modules_to_not_convert: list[str] | None 
                 else:
                     dense[key] = st.get_tensor(key)
     layers = {}
+    experts: dict[str, dict[int, dict[str, dict]]] = {}
+    for mod in list(raw):
+        # <base>.<e>.{gate,up,down}_proj without rotation buffers of its own + <base>.gate_up_weight_theta: an MoE expert
+        head, _, proj = mod.rpartition(".")
+        base, _, eid = head.rpartition(".")
+        if proj in ("gate_proj", "up_proj", "down_proj") and eid.isdigit() and "theta" not in raw[mod] and f"{base}.gate_up_weight_theta" in dense:
+            experts.setdefault(base, {}).setdefault(int(eid), {})[proj] = raw.pop(mod)
+    moe: dict[str, list[dict[str, ParoLayerBuffers]]] = {}
+    for base, by_id in experts.items():
+        rot = {}
+        for tag in ("gate_up", "down"):
+            th, pr, cs = (dense.pop(f"{base}.{tag}_weight_{leaf}") for leaf in ("theta", "pairs", "channel_scales"))
+            if check_pairs:
+                validate_pairs(pr, group)
+            rot[tag] = (th[None].contiguous(), pr[None].contiguous(), cs.reshape(1, 1, -1).contiguous())
+        blocks = []
+        for e in sorted(by_id):
+            t = by_id[e]
+            if set(t) != {"gate_proj", "up_proj", "down_proj"}:
+                raise ValueError(f"{base}.{e}: expert without all of gate_proj / up_proj / down_proj")
+
+            def part(p, tag):
+                b = t[p]
+                th, pr, cs = rot[tag]
+                n = int(b["qweight"].shape[1]) * 8
+                return ParoLayerBuffers(b["qweight"], b["qzeros"], b["scales"], th, pr, cs, [n], group, None)
+
+            blocks.append({"gate_up": merge_layers([part("gate_proj", "gate_up"), part("up_proj", "gate_up")]), "down": part("down_proj", "down")})
+        if sorted(by_id) != list(range(len(blocks))):
+            raise ValueError(f"{base}: expert ids are not 0..{len(blocks) - 1}")
+        moe[base] = blocks
     for mod, t in raw.items():
         missing = [k for k in QUANT_KEYS if k not in t]
         if missing:
@@ -180,7 +276,7 @@ def load_paro_checkpoint(model_dir, *, modules_to_not_convert: list[str] | None 
             validate_pairs(t["pairs"], group)
         layers[mod] = ParoLayerBuffers(t["qweight"], t["qzeros"], t["scales"], t["theta"][None].contiguous(), t["pairs"][None].contiguous(),
                                        t["channel_scales"].reshape(1, 1, K).contiguous(), [N], group, t.get("bias"))
-    return ParoCheckpoint({"quant_method": "paroquant", "bits": bits, "group_size": group, "krot": krot}, layers, dense)
+    return ParoCheckpoint({"quant_method": "paroquant", "bits": bits, "group_size": group, "krot": krot}, layers, dense, moe)
 
 
 def merge_layers(parts: list[ParoLayerBuffers]) -> ParoLayerBuffers:

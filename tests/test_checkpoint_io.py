@@ -136,3 +136,67 @@ def test_hf_quantizer_glue_replaces_and_loads(tmp_path):
     got = model.get_submodule(name)
     assert torch.equal(got.qweight, quantised[name].qweight) and torch.equal(got.pairs, quantised[name].pairs[0])
     assert torch.equal(got.channel_scales, quantised[name].channel_scales[0])
+
+
+# ------------------------------------------------------------------------------------------ MoE expert blocks (convert.py:281-406)
+MOE_GOLD = Path(__file__).parent / "golden" / "ref_convert_moe.npz"
+
+
+def test_moe_export_arithmetic_and_names_match_reference_converter():
+    """`moe_expert_buffers` + `moe_state_entries` against the reference's `_quantize_moe` / `_inject_quantized_moe_state_dict`
+    (tools/gen_convert_moe_golden.py; rotation stubbed by the identity on both sides: the integer work and the naming)."""
+    g = np.load(MOE_GOLD)
+    bits, group, krot, E, H, I = (int(v) for v in g["meta"])
+    st = {k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("in::")}
+    quant = {}
+    for tag, w in (("gate_up", st["gate_up_weight"]), ("down", st["down_weight"])):
+        quant[tag] = cio.quantize_rotated(w.reshape(-1, w.shape[-1]) * st[f"{tag}_channel_scales"].reshape(1, -1), st[f"{tag}_quantizer.scale"],
+                                          st[f"{tag}_quantizer.zero_point_float"], bits=bits, group_size=group)
+    proj = cio.moe_expert_buffers(quant["gate_up"], quant["down"], E)
+    rot = {}
+    for tag in ("gate_up", "down"):
+        rot[f"{tag}_weight_theta"] = torch.stack([st[f"{tag}_angles_grouped.{r}"] for r in range(krot)]).to(torch.float16)
+        rot[f"{tag}_weight_pairs"] = torch.stack([st[f"{tag}_pairs_grouped.{r}"] for r in range(krot)])
+        rot[f"{tag}_weight_channel_scales"] = (1.0 / st[f"{tag}_channel_scales"].reshape(1, -1)).to(torch.float16)
+    ours = cio.moe_state_entries("model.layers.3.mlp.experts", proj, rot)
+    ref = {k[5:]: g[k] for k in g.files if k.startswith("out::")}
+    assert set(ours) == set(ref) - {"other"}                      # the fused gate_up_proj / down_proj tensors are gone, the rest untouched
+    for k, v in ours.items():
+        assert np.array_equal(v.numpy(), ref[k]), k
+
+
+def test_moe_round_trip_through_the_loader(tmp_path):
+    """Expert modules carry no rotation of their own: the loader attaches the block's shared rotation and merges gate | up."""
+    E, H, I = 3, 256, 128
+    shared_gu = make_synthetic_layer(H, [I, I], seed=70)          # rotation of the hidden dim, shared by every expert
+    shared_d = make_synthetic_layer(I, [H], seed=71)
+    tensors, experts = {}, []
+    for e in range(E):
+        gu = make_synthetic_layer(H, [I, I], seed=80 + e)
+        d = make_synthetic_layer(I, [H], seed=90 + e)
+        experts.append((gu, d))
+        qw, qz = gu.qweight, gu.qzeros
+        for proj, sl, L in (("gate_proj", slice(0, I // 8), gu), ("up_proj", slice(I // 8, 2 * I // 8), gu)):
+            tensors[f"model.layers.0.mlp.experts.{e}.{proj}.qweight"] = qw[:, sl].contiguous()
+            tensors[f"model.layers.0.mlp.experts.{e}.{proj}.qzeros"] = qz[:, sl].contiguous()
+            tensors[f"model.layers.0.mlp.experts.{e}.{proj}.scales"] = gu.scales[:, sl.start * 8:sl.stop * 8].contiguous()
+        for leaf in ("qweight", "qzeros", "scales"):
+            tensors[f"model.layers.0.mlp.experts.{e}.down_proj.{leaf}"] = getattr(d, leaf)
+    for tag, L in (("gate_up", shared_gu), ("down", shared_d)):
+        tensors[f"model.layers.0.mlp.experts.{tag}_weight_theta"] = L.theta[0]
+        tensors[f"model.layers.0.mlp.experts.{tag}_weight_pairs"] = L.pairs[0]
+        tensors[f"model.layers.0.mlp.experts.{tag}_weight_channel_scales"] = L.channel_scales[0]
+    tensors["model.layers.0.mlp.gate.weight"] = torch.randn(E, H).half()       # the router: dense, untouched
+    cio.save_paro_checkpoint(tmp_path, tensors, base_config={"model_type": "qwen3_moe"})
+    ck = cio.load_paro_checkpoint(tmp_path)
+    assert not ck.layers and set(ck.experts) == {"model.layers.0.mlp.experts"} and set(ck.dense) == {"model.layers.0.mlp.gate.weight"}
+    blocks = ck.experts["model.layers.0.mlp.experts"]
+    assert len(blocks) == E
+    for e, b in enumerate(blocks):
+        gu, d = experts[e]
+        assert b["gate_up"].part_sizes == [I, I] and b["down"].part_sizes == [H]
+        assert torch.equal(b["gate_up"].qweight, gu.qweight) and torch.equal(b["gate_up"].scales, gu.scales)
+        assert torch.equal(b["down"].qweight, d.qweight)
+        for p in range(2):                                        # both partitions carry the block's shared rotation
+            assert torch.equal(b["gate_up"].theta[p], shared_gu.theta[0]) and torch.equal(b["gate_up"].pairs[p], shared_gu.pairs[0])
+        assert torch.equal(b["down"].pairs[0], shared_d.pairs[0]) and torch.equal(b["down"].channel_scales.reshape(-1), shared_d.channel_scales[0].reshape(-1))
