@@ -22,7 +22,7 @@ def _opt_state(n_out, k_in, seed, group=128, krot=8):
     g = torch.Generator().manual_seed(seed)
     w = torch.randn(n_out, k_in, generator=g) * 0.05
     pairs = torch.stack([torch.cat([torch.randperm(group, generator=g) for _ in range(k_in // group)]) for _ in range(krot)]).to(torch.int16)
-    theta = (torch.rand(krot, k_in // 2, generator=g) - 0.5) * 1.5
+    theta = torch.randn(krot, k_in // 2, generator=g) * 0.3      # the angle scale of make_synthetic_layer
     cs = 0.5 + torch.rand(1, k_in, generator=g)
     st = {"weight": w, "n_bits": torch.tensor(4), "group_size": torch.tensor(group), "channel_scales": cs}
     for r in range(krot):
