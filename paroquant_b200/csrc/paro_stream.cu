@@ -170,7 +170,9 @@ __device__ __forceinline__ void seg_range(const SegWalk &w, int k, int &ra, int 
   rb = ra + w.ng;
 }
 
-// {value, tag} words: relaxed 8-byte accesses at GPU scope (one access, never torn); the tag validates the value
+// {value, tag} words: relaxed, naturally aligned 8-byte vector accesses at GPU scope; the tag validates the value.  (The hardware
+// performs an aligned .v2.u32 as one 8-byte transaction -- the property NCCL's LL protocol is built on.  Scalar .u64 accesses,
+// which the PTX model guarantees to be single-copy atomic, were measured: same results, but the chain got 13 % slower.)
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *ptr) {
   uint32_t v;
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
@@ -574,10 +576,11 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 6), 1) stream_kernel(const __
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ================= epilogue group (4 warps, TMEM lane quarter = warp % 4): D -> {partial, tag} slot; the block's
-    // REDUCER (the contributor that holds the block's last round in the last K slice) polls the other contributors'
-    // slots, adds them in fixed order, finishes the block and publishes it for the next step, again as {value, tag} pairs.
-    // No fences, no counters: every 8-byte word carries the launch's tag, a reader retries until the tag matches.
+    // ================= epilogue group (4 warps, TMEM lane quarter = warp % 4; each warp works alone on its 32 columns):
+    // D -> {partial, tag} slot; the block's REDUCER (in K slice `block mod c`, the contributor that holds the block's last round)
+    // looks at the other contributors' slots, adds them in fixed order, finishes the block and publishes it for the next step,
+    // again as {value, tag} words.  No fences, no counters: every 8-byte word carries the launch's tag, a reader retries
+    // until the tag matches.
     const int q = warp & 3;
     const int L128 = 32 * q + lane;
     const uint32_t lane_base = static_cast<uint32_t>(32 * q) << 16;
