@@ -31,7 +31,8 @@ int prepack_launch(const paro_linear_shape &s, const Layout &L, const int32_t *q
 int unpack_dense_launch(const paro_linear_shape &s, const Layout &L, const void *packed, void *W, cudaStream_t stream);
 bool decode_supported(const Layout &L, int64_t M);
 int decode_forward(const paro_linear_shape &s, const Layout &L, const void *packed, const void *x, int64_t M,
-                   const void *bias, void *y, cudaStream_t stream);
+                   const void *bias, void *y, void *scratch, size_t scratch_bytes, cudaStream_t stream);
+size_t decode_scratch_bytes(const Layout &L, int64_t max_m);
 int decode_trace_read(unsigned long long *host, int max_ctas);
 int decode_debug_plan(const Layout &L, int64_t M, int sets, int sms, const int32_t *resident4, int32_t *out20);
 bool stream_supported(const Layout &L, int64_t M);
@@ -117,6 +118,10 @@ size_t paro_workspace_bytes(const paro_linear_shape *shape, int64_t max_m) {
   // head: sync words + block counters of the small-M kernel (zero between calls); behind them scratch: the partial slots
   // of the small-M kernel or the rotated activations of the M > 16 path
   size_t b = stream_workspace_bytes(L, max_m);
+  {
+    const size_t d = stream_sync_bytes(L) + decode_scratch_bytes(L, max_m);
+    if (d > b) b = d;
+  }
   if (max_m > small_m_max()) {
     const size_t g = stream_sync_bytes(L) + gemm_workspace_bytes(L, max_m);
     if (g > b) b = g;
@@ -145,7 +150,9 @@ int paro_linear_forward(const paro_linear_shape *shape, const void *packed, cons
     // cluster kernel has no launch plan (very long K) and for chains / tensor-parallel steps (paro_chain_forward).
     static const bool stream_only = [] { const char *v = getenv("PARO_DECODE_STREAM"); return v && *v && atoi(v) != 0; }();
     if (!stream_only) {
-      const int rc = decode_forward(*shape, L, packed, x, M, bias, y, st);
+      const size_t head = stream_sync_bytes(L);   // the pre-rotated rows of the M >= 4 pre-pass live behind the epoch word
+      const int rc = decode_forward(*shape, L, packed, x, M, bias, y, static_cast<uint8_t *>(workspace) + head,
+                                    workspace_bytes > head ? workspace_bytes - head : 0, st);
       if (rc != PARO_EUNSUPPORTED) return rc;
     }
     return stream_linear_forward(*shape, L, packed, x, M, bias, y, workspace, workspace_bytes, st);

@@ -65,6 +65,8 @@ struct DecParams {
   int n_parts, groups, krot;
   int c, c_shift;                 // cluster size (K slices of this launch), log2
   int nstages, rot_bytes, rot_warps, trace;   // rot_warps: worker warps that take rotation tasks (each owns one rot_bytes tile)
+  int pre_rotated;                // x is the pre-pass's output: [n_parts][M][K], already scaled and rotated (no stages here)
+  long long x_part_stride;        // elements between partitions of a pre-rotated x (0 otherwise)
   int xb_off, rot_off, recv_off, bar_off;   // shared-memory carve-up (bytes)
   int part_col_begin[PARO_MAX_PARTS + 1];
   int part_block_begin[PARO_MAX_PARTS + 1];
@@ -101,6 +103,7 @@ struct DecRotMeta {
 
 __device__ __forceinline__ void dec_fetch_meta(const DecParams &p, int part, int gk, int lane, DecRotMeta &rm) {
   rm.meta = p.packed + p.meta_off + (static_cast<size_t>(part) * p.groups + gk) * p.meta_group_bytes;
+  if (p.pre_rotated) return;   // no rotation tasks at all
   rm.csw = *reinterpret_cast<const uint2 *>(rm.meta + p.krot * 256 + 8 * lane);
   if (p.krot == 8) {
 #pragma unroll
@@ -112,10 +115,11 @@ __device__ __forceinline__ void dec_fetch_meta(const DecParams &p, int part, int
 }
 
 template <typename T, int ROWS>
-__device__ __forceinline__ void dec_rotate_task(const DecParams &p, const DecRotMeta &rm, int gk, int m0, int lane, uint32_t rot, uint32_t xb_group,
-                                                long long t_entry) {
+__device__ __forceinline__ void dec_rotate_task(const DecParams &p, const DecRotMeta &rm, const void *xpart, int gk, int m0, int lane, uint32_t rot,
+                                                uint32_t xb_group, long long t_entry) {
   uint2 raw[ROWS];
-  load_x<T, ROWS>(p, gk, lane, raw, m0);
+  struct { const void *x; int M, K; } px = {xpart, p.M, p.K};   // my partition's rows (a pre-rotated x has one copy per partition)
+  load_x<T, ROWS>(px, gk, lane, raw, m0);
   scale_and_stage<T, ROWS>(rot, lane, raw, rm.csw);
   __syncwarp();
   if (p.trace && threadIdx.x == 0 && blockIdx.x < kDecTraceCtas) g_dec_trace[blockIdx.x * kDecTraceSlots + 0] = clock64() - t_entry;
@@ -150,10 +154,11 @@ __device__ __forceinline__ void dec_rotate_task(const DecParams &p, const DecRot
 template <typename T, int ROWS>
 __device__ __forceinline__ void dec_prologue(const DecParams &p, DecRotMeta &rm, int part, int g_begin, int ntasks, int nq, int wi, int nwarps,
                                              int lane, uint32_t rot, uint32_t xb, long long t_entry) {
+  const void *xpart = static_cast<const T *>(p.x) + static_cast<long long>(part) * p.x_part_stride;
   for (int t = wi; t < ntasks; t += nwarps) {
     const int gi = t / nq, rq = t - gi * nq;
     if (t != wi) dec_fetch_meta(p, part, g_begin + gi, lane, rm);
-    dec_rotate_task<T, ROWS>(p, rm, g_begin + gi, rq * ROWS, lane, rot, xb + gi * (kDecN * 256), t_entry);
+    dec_rotate_task<T, ROWS>(p, rm, xpart, g_begin + gi, rq * ROWS, lane, rot, xb + gi * (kDecN * 256), t_entry);
   }
 }
 
@@ -177,6 +182,7 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
   const uint32_t bar_wfull = bars, bar_wempty = bars + 8 * kDecMaxStages;
   const uint32_t bar_afull = bars + 16 * kDecMaxStages, bar_afree = bar_afull + 64;
   const uint32_t bar_dfull = bar_afull + 128, bar_dfree = bar_afull + 192, bar_xb = bar_afull + 208, tmem_slot = bar_afull + 216;
+  const uint32_t bar_xload = bar_afull + 224;   // pre-rotated x: one bulk copy fills the whole B operand
   constexpr uint32_t d_col0 = 64 * SETS;
 
   // ---- my range of 128-column blocks (within one partition) and my K-slice (whole groups, ragged)
@@ -219,7 +225,10 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
       mbar_init(bar_dfull + 8 * lane, 1);
     }
     if (lane < 2) mbar_init(bar_dfree + 8 * lane, 4);
-    if (lane == 0) mbar_init(bar_xb, kWorkers);
+    if (lane == 0) {
+      mbar_init(bar_xb, kWorkers);
+      mbar_init(bar_xload, 1);
+    }
     fence_mbar_init();
   }
   if (warp == kWorkers + 1) {
@@ -258,6 +267,19 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
     // `lane == 0` branch every tcgen05.mma was wrapped in a divergence loop (~15 instructions, ~120 cycles per MMA,
     // tools/mma_probe.cu) and the single issuing thread, not the tensor pipe, bounded the kernel.
     const uint32_t idesc = instr_desc<T>(kDecN);
+    if (p.pre_rotated) {
+      // the pre-pass (paro_rotate.cu, tiled for 16 rows) wrote x_rot in exactly the B-operand order of this kernel, zero padding
+      // rows included: the K-slice's groups are ONE contiguous range -> one bulk copy, no rotation tasks, no proxy fence
+      pdl_wait();   // ... written by the previous kernel in the stream
+      if (elect_one()) {
+        const uint32_t bytes = static_cast<uint32_t>(ng) * (kDecN * 256);
+        mbar_arrive_expect_tx(bar_xload, bytes);
+        bulk_g2s(xb, static_cast<const uint8_t *>(p.x) + (static_cast<size_t>(part) * p.x_part_stride + static_cast<size_t>(g_begin) * (kDecN * kGroup)) * 2,
+                 bytes, bar_xload, policy_evict_first());
+      }
+      __syncwarp();
+      mbar_wait(bar_xload, 0);
+    }
     mbar_wait(bar_xb, 0);   // B operand rows written (generic proxy) and fenced by the workers
     const uint64_t desc_hi = smem_desc_kmajor(0, kDecN * 16, 128);   // everything but the start address
     int set = 0, use = 0, j = 0, gi = 0;
@@ -285,14 +307,14 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
     const uint32_t lane_base = static_cast<uint32_t>(32 * q) << 16;
     // rows [M, 16) of every group are the zero padding of the N = 16 MMA: all workers clear the B operand before the
     // dependency wait (it does not depend on x); the rotation tasks then write only token rows
-    if (p.M < kDecN) {
+    if (p.M < kDecN && !p.pre_rotated) {
       for (int i = threadIdx.x; i < ng * (kDecN * 16); i += 32 * kWorkers) sts128u(xb + i * 16, make_uint4(0u, 0u, 0u, 0u));
       named_bar_sync(1, 32 * kWorkers);
     }
     DEC_TRACE(2);
-    pdl_wait();  // x may have been written by the previous kernel
+    if (!p.pre_rotated) pdl_wait();  // x may have been written by the previous kernel (pre-rotated: the MMA warp fetches it)
     DEC_TRACE(3);
-    if (wi < ntasks && wi < p.rot_warps) {
+    if (!p.pre_rotated && wi < ntasks && wi < p.rot_warps) {
       const uint32_t rot = smem0 + p.rot_off + wi * p.rot_bytes;
       const int M = p.M, rw = p.rot_warps;
       if (M == 1) dec_prologue<T, 1>(p, rm, part, g_begin, ntasks, nq, wi, rw, lane, rot, xb, t_entry);
@@ -668,16 +690,50 @@ static int launch_decode(DecParams &p, const Layout &L, int sms, cudaStream_t st
 
 bool decode_supported(const Layout &L, int64_t M) { return M >= 1 && M <= 16 && L.groups >= 1; }
 
+// From 5 rows on (3 when K >= 8192) the rotation runs ONCE, in a pre-pass (paro_rotate.cu: rotate_small_kernel, one launch for all
+// partitions, ~2.5 us) that writes x_rot in this kernel's B-operand order, and the kernel fetches its K slice with one bulk copy.
+// Inside the kernel a 4-row rotation task is ~1000 dependent instructions of one warp (7-14 k cycles with 20 warps contending) and
+// at M = 16 a CTA has 32-56 of them: 28 k of o_proj's 40 k cycles, 48 k of down_proj's 80 k (tools/trace_decode.py).  Measured
+// (us, in-kernel -> pre-pass): M = 16: o 21.7 -> 13.4, qkv 18.2 -> 16.4, gate_up 38.1 -> 29.1, down 42.3 -> 23.8; M = 8: 14.0 ->
+// 11.8, 16.7 -> 15.0, 29.7 -> 27.5, 38.2 -> 20.3; M = 4: o 10.0 -> 11.4 (stays in-kernel), down 25.1 -> 18.7.
+static int dec_prerot_knob() {
+  static const int v = dec_env_int("PARO_DECODE_PREROT_M", 0);   // 0: the rule below; n >= 2: from n rows on; 1: never
+  return v;
+}
+static bool decode_wants_prerot(const Layout &L, int64_t M) {
+  const int k = dec_prerot_knob();
+  if (k == 1) return false;
+  if (k >= 2) return M >= k;
+  return M >= 5 || (M >= 3 && L.groups >= 64);
+}
+size_t decode_scratch_bytes(const Layout &L, int64_t max_m) {
+  bool any = false;
+  for (int64_t m = 1; m <= (max_m < 16 ? max_m : 16); ++m) any = any || decode_wants_prerot(L, m);
+  return any ? static_cast<size_t>(L.n_parts) * kDecN * L.K * 2 : 0;
+}
+
+int rotate_small_launch(const void *x, void *out, const void *raw_base, long long raw_part_bytes, int n_parts, int64_t M, int K, int krot,
+                        int dtype, cudaStream_t stream);
+
 int decode_forward(const paro_linear_shape &s, const Layout &L, const void *packed, const void *x, int64_t M,
-                   const void *bias, void *y, cudaStream_t stream) {
+                   const void *bias, void *y, void *scratch, size_t scratch_bytes, cudaStream_t stream) {
   int dev = 0;
   PARO_CUDA_OK(cudaGetDevice(&dev));
   static thread_local int sms_of[64] = {};   // SM count per device, asked once
   if (!sms_of[dev & 63]) PARO_CUDA_OK(cudaDeviceGetAttribute(&sms_of[dev & 63], cudaDevAttrMultiProcessorCount, dev));
   const int sms = sms_of[dev & 63];
+  const size_t part_bytes = static_cast<size_t>(kDecN) * L.K * 2;   // 16 rows (zero padded) x K of T, B-operand order
+  const bool prerot = decode_wants_prerot(L, M) && scratch && scratch_bytes >= L.n_parts * part_bytes;
+  if (prerot) {   // one launch for all partitions (paro_rotate.cu: rotate_small_kernel)
+    const int rc = rotate_small_launch(x, scratch, static_cast<const uint8_t *>(packed) + L.raw_off, static_cast<long long>(L.raw_part_bytes), L.n_parts, M,
+                                       L.K, L.krot, s.dtype, stream);
+    if (rc) return rc;
+  }
   DecParams p = {};
   p.packed = static_cast<const uint8_t *>(packed);
-  p.x = x; p.y = y; p.bias = bias;
+  p.x = prerot ? scratch : x; p.y = y; p.bias = bias;
+  p.pre_rotated = prerot ? 1 : 0;
+  p.x_part_stride = prerot ? static_cast<long long>(kDecN) * L.K : 0;
   p.M = static_cast<int>(M); p.K = L.K; p.N = L.N;
   p.n_parts = L.n_parts; p.groups = L.groups; p.krot = L.krot;
   p.rot_bytes = dec_rot_bytes(M);

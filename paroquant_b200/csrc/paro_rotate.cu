@@ -211,6 +211,135 @@ __global__ void __launch_bounds__(128) rotate_kernel(const T *__restrict__ x, T 
   }
 }
 
+
+// ------------------------------------------------------------------ pre-pass of the small-M kernel (8..16 rows, paro_decode.cu)
+// ONE launch for all partitions of a merged linear: warp = (partition, group, block of 8 rows); output in the B-operand order
+// of the small-M kernel (16 token rows, rows >= M zero).  Same arithmetic as rotate_kernel; what differs is latency: the pair
+// indices and angles of all (<= 8 at a time) rotations are fetched up front, so the launch costs one global-load round trip
+// instead of one per stage (rotate_kernel at 16 rows: ~7 us, almost all of it eight dependent L2 / DRAM latencies).
+template <typename T>
+__global__ void __launch_bounds__(128) rotate_small_kernel(const T *__restrict__ x, T *__restrict__ out, const uint8_t *__restrict__ raw_base,
+                                                           long long raw_part_bytes, long long out_part_elems, int M, int K, int krot,
+                                                           int n_parts) {
+  constexpr int G = 128, RB = 8;
+  __shared__ __align__(16) uint4 tile[4][G];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int groups = K / G;
+  const int task = blockIdx.x * 4 + warp;          // (part, row block, group)
+  if (task >= n_parts * 2 * groups) return;
+  const int g = task % groups, rb = (task / groups) & 1, part = task / (2 * groups);
+  const uint8_t *raw = raw_base + part * raw_part_bytes;
+  const int16_t *idx = reinterpret_cast<const int16_t *>(raw);
+  const T *theta = reinterpret_cast<const T *>(raw + static_cast<size_t>(krot) * K * 2);
+  const T *scales = reinterpret_cast<const T *>(raw + static_cast<size_t>(krot) * K * 3);
+  T *o = out + part * out_part_elems;
+  uint4 *rot = tile[warp];
+  const int row0 = rb * RB;
+  if (row0 >= M) {   // a block of padding rows: zeros, in place
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      const int n = row0 + r, k = g * G + lane * 4;
+      const int64_t off = static_cast<int64_t>(k >> 4) * 256 + ((k >> 3) & 1) * 128 + (n >> 3) * 64 + (n & 7) * 8 + (k & 7);
+      *reinterpret_cast<uint2 *>(o + off) = make_uint2(0u, 0u);
+    }
+    return;
+  }
+  // ---- everything this warp will need from global memory, issued together
+  uint2 xr[RB];
+#pragma unroll
+  for (int r = 0; r < RB; ++r)
+    xr[r] = row0 + r < M ? *reinterpret_cast<const uint2 *>(x + static_cast<int64_t>(row0 + r) * K + g * G + lane * 4) : make_uint2(0u, 0u);
+  const uint2 scw = *reinterpret_cast<const uint2 *>(scales + g * G + lane * 4);
+  for (int r0 = 0; r0 < krot; r0 += 8) {
+    int ij[8][2];
+    uint32_t th[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (r0 + r < krot) {
+        const uint2 w = *reinterpret_cast<const uint2 *>(idx + static_cast<int64_t>(r0 + r) * K + g * G + 4 * lane);   // pairs 2 lane, 2 lane + 1
+        ij[r][0] = static_cast<int>(w.x);
+        ij[r][1] = static_cast<int>(w.y);
+        th[r] = *reinterpret_cast<const uint32_t *>(theta + static_cast<int64_t>(r0 + r) * (K / 2) + g * (G / 2) + 2 * lane);
+      }
+    }
+    if (r0 == 0) {
+      // scale (one rounding, rotation.cuh:112-113), transpose into rot[channel]
+      const T *ps = reinterpret_cast<const T *>(&scw);
+      T v[RB][4];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const T *pr = reinterpret_cast<const T *>(&xr[r]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[r][c] = __hmul(pr[c], ps[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 w;
+        T *pw = reinterpret_cast<T *>(&w);
+#pragma unroll
+        for (int r = 0; r < RB; ++r) pw[r] = v[r][c];
+        rot[rot_slot(lane * 4 + c)] = w;
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (r0 + r < krot) {
+        const float2 t2 = Traits<T>::to_float2(unpack2<T>(th[r]));
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          float sn, cs;
+          __sincosf(q ? t2.y : t2.x, &sn, &cs);
+          const int pi = ij[r][q] & 0xFFFF, pj = (ij[r][q] >> 16) & 0xFFFF;
+          uint4 vi = rot[rot_slot(pi)], vj = rot[rot_slot(pj)];
+          pair_update<T>(vi, vj, cs, sn);
+          rot[rot_slot(pi)] = vi;
+          rot[rot_slot(pj)] = vj;
+        }
+        __syncwarp();
+      }
+    }
+  }
+  // ---- transpose out into the B-operand order: [k16 step][k half][row / 8][row % 8][8 elements]
+  T v[RB][4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint4 w = rot[rot_slot(lane * 4 + c)];
+    const T *pw = reinterpret_cast<const T *>(&w);
+#pragma unroll
+    for (int r = 0; r < RB; ++r) v[r][c] = pw[r];
+  }
+#pragma unroll
+  for (int r = 0; r < RB; ++r) {
+    const int n = row0 + r, k = g * G + lane * 4;
+    uint2 w = make_uint2(0u, 0u);
+    if (n < M) {
+      T *pw = reinterpret_cast<T *>(&w);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) pw[c] = v[r][c];
+    }
+    const int64_t off = static_cast<int64_t>(k >> 4) * 256 + ((k >> 3) & 1) * 128 + (n >> 3) * 64 + (n & 7) * 8 + (k & 7);
+    *reinterpret_cast<uint2 *>(o + off) = w;
+  }
+}
+
+// all partitions, <= 16 rows, metadata in the layout's reference-format region (theta and channel scales already of dtype T)
+int rotate_small_launch(const void *x, void *out, const void *raw_base, long long raw_part_bytes, int n_parts, int64_t M, int K, int krot,
+                        int dtype, cudaStream_t stream) {
+  const int tasks = n_parts * 2 * (K / 128);
+  const int blocks = (tasks + 3) / 4;
+  if (dtype == PARO_F16)
+    rotate_small_kernel<__half><<<blocks, 128, 0, stream>>>(static_cast<const __half *>(x), static_cast<__half *>(out), static_cast<const uint8_t *>(raw_base),
+                                                           raw_part_bytes, 16ll * K, static_cast<int>(M), K, krot, n_parts);
+  else
+    rotate_small_kernel<__nv_bfloat16><<<blocks, 128, 0, stream>>>(static_cast<const __nv_bfloat16 *>(x), static_cast<__nv_bfloat16 *>(out),
+                                                                  static_cast<const uint8_t *>(raw_base), raw_part_bytes, 16ll * K, static_cast<int>(M), K,
+                                                                  krot, n_parts);
+  PARO_CUDA_OK(cudaGetLastError());
+  note_launches(1);
+  return PARO_OK;
+}
+
 template <typename T>
 static int launch_T(const void *x, void *out, const int16_t *idx, const void *theta, int theta_dtype,
                     const void *scales, int scales_dtype, int64_t M, int K, int krot, int G, cudaStream_t stream,

@@ -210,7 +210,7 @@ __device__ __forceinline__ void rotate_stage(uint32_t rot, uint32_t idxw, float 
 // this lane's 4 channels of the group for all rows: raw x (no dependence on the rotation metadata)
 template <typename T, int ROWS, typename P>
 __device__ __forceinline__ void load_x(const P &p, int gk, int lane, uint2 (&raw)[ROWS], int m0 = 0) {
-  const T *xg = static_cast<const T *>(p.x) + gk * kGroup + 4 * lane;
+  const T *xg = static_cast<const T *>(p.x) + gk * kGroup + 4 * lane;   // (p.x already points at the CTA's partition when pre-rotated)
 #pragma unroll
   for (int m = 0; m < ROWS; ++m) {
     raw[m] = make_uint2(0u, 0u);
