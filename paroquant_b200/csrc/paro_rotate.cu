@@ -212,22 +212,23 @@ __global__ void __launch_bounds__(128) rotate_kernel(const T *__restrict__ x, T 
 }
 
 
-// ------------------------------------------------------------------ pre-pass of the small-M kernel (8..16 rows, paro_decode.cu)
+// ------------------------------------------------------------------ pre-pass of the tcgen05 kernels (paro_decode.cu from 5 rows, paro_gemm.cu)
 // ONE launch for all partitions of a merged linear: warp = (partition, group, block of 8 rows); output in the B-operand order
-// of the small-M kernel (16 token rows, rows >= M zero).  Same arithmetic as rotate_kernel; what differs is latency: the pair
+// of the consumer (tiles of nt tokens, rows >= M zero).  Same arithmetic as rotate_kernel; what differs is latency: the pair
 // indices and angles of all (<= 8 at a time) rotations are fetched up front, so the launch costs one global-load round trip
 // instead of one per stage (rotate_kernel at 16 rows: ~7 us, almost all of it eight dependent L2 / DRAM latencies).
 template <typename T>
 __global__ void __launch_bounds__(128) rotate_small_kernel(const T *__restrict__ x, T *__restrict__ out, const uint8_t *__restrict__ raw_base,
-                                                           long long raw_part_bytes, long long out_part_elems, int M, int K, int krot,
-                                                           int n_parts) {
+                                                           long long raw_part_bytes, long long out_part_elems, int M, int M_store, int nt, int K,
+                                                           int krot, int n_parts) {
   constexpr int G = 128, RB = 8;
   __shared__ __align__(16) uint4 tile[4][G];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int groups = K / G;
-  const int task = blockIdx.x * 4 + warp;          // (part, row block, group)
-  if (task >= n_parts * 2 * groups) return;
-  const int g = task % groups, rb = (task / groups) & 1, part = task / (2 * groups);
+  const int row_blocks = M_store / RB;
+  const long long task = static_cast<long long>(blockIdx.x) * 4 + warp;          // (part, row block, group)
+  if (task >= static_cast<long long>(n_parts) * row_blocks * groups) return;
+  const int g = static_cast<int>(task % groups), rb = static_cast<int>((task / groups) % row_blocks), part = static_cast<int>(task / (static_cast<long long>(row_blocks) * groups));
   const uint8_t *raw = raw_base + part * raw_part_bytes;
   const int16_t *idx = reinterpret_cast<const int16_t *>(raw);
   const T *theta = reinterpret_cast<const T *>(raw + static_cast<size_t>(krot) * K * 2);
@@ -235,13 +236,15 @@ __global__ void __launch_bounds__(128) rotate_small_kernel(const T *__restrict__
   T *o = out + part * out_part_elems;
   uint4 *rot = tile[warp];
   const int row0 = rb * RB;
+  // B-operand order of the tcgen05 kernels: [token block of nt][k16 step][k half][row / 8][row % 8][8 elements]
+  auto tiled = [&](int m, int k) -> int64_t {
+    const int tb = m / nt, n = m - tb * nt;
+    return (static_cast<int64_t>(tb) * (K / 16) + (k >> 4)) * (static_cast<int64_t>(nt) * 16) + ((k >> 3) & 1) * (nt * 8) + (n >> 3) * 64 + (n & 7) * 8 +
+           (k & 7);
+  };
   if (row0 >= M) {   // a block of padding rows: zeros, in place
 #pragma unroll
-    for (int r = 0; r < RB; ++r) {
-      const int n = row0 + r, k = g * G + lane * 4;
-      const int64_t off = static_cast<int64_t>(k >> 4) * 256 + ((k >> 3) & 1) * 128 + (n >> 3) * 64 + (n & 7) * 8 + (k & 7);
-      *reinterpret_cast<uint2 *>(o + off) = make_uint2(0u, 0u);
-    }
+    for (int r = 0; r < RB; ++r) *reinterpret_cast<uint2 *>(o + tiled(row0 + r, g * G + lane * 4)) = make_uint2(0u, 0u);
     return;
   }
   // ---- everything this warp will need from global memory, issued together
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(128) rotate_small_kernel(const T *__restrict__
       }
     }
   }
-  // ---- transpose out into the B-operand order: [k16 step][k half][row / 8][row % 8][8 elements]
+  // ---- transpose out
   T v[RB][4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -318,23 +321,26 @@ __global__ void __launch_bounds__(128) rotate_small_kernel(const T *__restrict__
 #pragma unroll
       for (int c = 0; c < 4; ++c) pw[c] = v[r][c];
     }
-    const int64_t off = static_cast<int64_t>(k >> 4) * 256 + ((k >> 3) & 1) * 128 + (n >> 3) * 64 + (n & 7) * 8 + (k & 7);
-    *reinterpret_cast<uint2 *>(o + off) = w;
+    *reinterpret_cast<uint2 *>(o + tiled(n, k)) = w;
   }
 }
 
-// all partitions, <= 16 rows, metadata in the layout's reference-format region (theta and channel scales already of dtype T)
-int rotate_small_launch(const void *x, void *out, const void *raw_base, long long raw_part_bytes, int n_parts, int64_t M, int K, int krot,
-                        int dtype, cudaStream_t stream) {
-  const int tasks = n_parts * 2 * (K / 128);
-  const int blocks = (tasks + 3) / 4;
+// all partitions in one launch; metadata in the layout's reference-format region (theta and channel scales already of dtype T);
+// output per partition: M_store rows (a multiple of 8; rows >= M zero) in tiles of `nt` tokens
+int rotate_small_launch(const void *x, void *out, const void *raw_base, long long raw_part_bytes, int n_parts, int64_t M, int64_t M_store, int nt,
+                        int K, int krot, int dtype, cudaStream_t stream) {
+  const long long tasks = static_cast<long long>(n_parts) * (M_store / 8) * (K / 128);
+  const long long blocks = (tasks + 3) / 4;
+  if (blocks > 0x7FFFFFFF) { set_error("rotate: too many rows"); return PARO_EINVAL; }
+  const long long part_elems = static_cast<long long>(M_store) * K;
   if (dtype == PARO_F16)
-    rotate_small_kernel<__half><<<blocks, 128, 0, stream>>>(static_cast<const __half *>(x), static_cast<__half *>(out), static_cast<const uint8_t *>(raw_base),
-                                                           raw_part_bytes, 16ll * K, static_cast<int>(M), K, krot, n_parts);
+    rotate_small_kernel<__half><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(static_cast<const __half *>(x), static_cast<__half *>(out),
+                                                                                  static_cast<const uint8_t *>(raw_base), raw_part_bytes, part_elems,
+                                                                                  static_cast<int>(M), static_cast<int>(M_store), nt, K, krot, n_parts);
   else
-    rotate_small_kernel<__nv_bfloat16><<<blocks, 128, 0, stream>>>(static_cast<const __nv_bfloat16 *>(x), static_cast<__nv_bfloat16 *>(out),
-                                                                  static_cast<const uint8_t *>(raw_base), raw_part_bytes, 16ll * K, static_cast<int>(M), K,
-                                                                  krot, n_parts);
+    rotate_small_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(
+        static_cast<const __nv_bfloat16 *>(x), static_cast<__nv_bfloat16 *>(out), static_cast<const uint8_t *>(raw_base), raw_part_bytes, part_elems,
+        static_cast<int>(M), static_cast<int>(M_store), nt, K, krot, n_parts);
   PARO_CUDA_OK(cudaGetLastError());
   note_launches(1);
   return PARO_OK;
