@@ -58,9 +58,9 @@ typedef void *paro_stream_t; /* cudaStream_t */
  * Mirrors what ParoQuantLinearMethod.create_weights receives (plugin.py:173-206):
  * in_features = input_size_per_partition, part_sizes = output_partition_sizes.        */
 typedef struct paro_linear_shape {
-  int32_t in_features;                 /* K, multiple of group_size                    */
+  int32_t in_features;                 /* K, multiple of 128                           */
   int32_t out_features;                /* N = sum(part_sizes)                          */
-  int32_t group_size;                  /* quantisation == rotation group; 128          */
+  int32_t group_size;                  /* quantisation == rotation group; 64 or 128    */
   int32_t krot;                        /* rotations per group (1..16); 8 in checkpoints */
   int32_t n_parts;                     /* 1, or 3 for QKV / 2 for gate_up              */
   int32_t part_sizes[PARO_MAX_PARTS];  /* each a multiple of 16                        */

@@ -206,8 +206,8 @@ def find_quantized_modules(model_dir) -> set[str]:
 
 
 def load_paro_checkpoint(model_dir, *, modules_to_not_convert: list[str] | None = None, check_pairs: bool = True) -> ParoCheckpoint:
-    """Read every ``*.safetensors`` of a converted model directory.  Raises on a config that is not ParoQuant INT4 g128
-    (the only format the fused kernels implement) and on incomplete / inconsistent quantised modules."""
+    """Read every ``*.safetensors`` of a converted model directory.  Raises on a config that is not ParoQuant INT4 with groups of 64 or 128
+    (the formats the fused kernels implement) and on incomplete / inconsistent quantised modules."""
     from safetensors import safe_open
     d = Path(model_dir)
     cfg_file = d / "config.json"
@@ -215,8 +215,8 @@ def load_paro_checkpoint(model_dir, *, modules_to_not_convert: list[str] | None 
     if qcfg.get("quant_method") != "paroquant":
         raise ValueError(f"{d}: quantization_config.quant_method is {qcfg.get('quant_method')!r}, expected 'paroquant'")
     bits, group, krot = int(qcfg.get("bits", 4)), int(qcfg.get("group_size", 128)), int(qcfg.get("krot", 8))
-    if bits != 4 or group != 128:
-        raise ValueError(f"{d}: bits={bits}, group_size={group}: the B200 kernels implement INT4 group-128 only")
+    if bits != 4 or group not in (64, 128):
+        raise ValueError(f"{d}: bits={bits}, group_size={group}: the B200 kernels implement INT4 with group_size 64 or 128 only")
     quantized = find_quantized_modules(d)
     if modules_to_not_convert:
         quantized -= set(modules_to_not_convert)

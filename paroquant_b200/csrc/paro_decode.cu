@@ -44,7 +44,7 @@ constexpr int kDecMaxStages = 24;
 constexpr int kDecTmemCols = 512;
 constexpr int kDecN = 16;            // MMA N: token rows, zero-padded (M_mma = 128 needs N % 16 == 0)
 constexpr int kDecSmemLimit = 227 * 1024;
-constexpr int kDecStage = kBlockBytes;   // one record per ring stage (8576 bytes, a multiple of 64)
+// one record per ring stage: 8576 bytes (group_size 128) or 8960 (group_size 64), both multiples of 64 -> DecParams::rec_bytes
 
 constexpr int kDecTraceSlots = 12;
 constexpr int kDecTraceCtas = 200;       // rows 200.. of the trace double as a per-round log of CTA 0 (issued / full / consumed)
@@ -65,6 +65,7 @@ struct DecParams {
   int n_parts, groups, krot;
   int c, c_shift;                 // cluster size (K slices of this launch), log2
   int nstages, rot_bytes, rot_warps, trace;   // rot_warps: worker warps that take rotation tasks (each owns one rot_bytes tile)
+  int rec_bytes, q2;              // record (= ring stage) size; q2: group_size 64, two scale / zero sets per record (paro_layout.h)
   int pre_rotated;                // x is the pre-pass's output: [n_parts][M][K], already scaled and rotated (no stages here)
   long long x_part_stride;        // elements between partitions of a pre-rotated x (0 otherwise)
   int xb_off, rot_off, recv_off, bar_off;   // shared-memory carve-up (bytes)
@@ -202,8 +203,9 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
   const int nrounds = nj * ng;
   // first output column of my first block, and the end of my partition (a last partial block is masked at the stores)
   const int n_first = p.part_col_begin[part] + cb_begin * kBlockN, n_end = p.part_col_begin[part + 1];
-  // record of (block j, group gi) of mine: rec0 + (j * groups + gi) * kBlockBytes
-  const uint8_t *rec0 = p.packed + p.rec_off + (static_cast<size_t>(p.part_block_begin[part] + cb_begin) * p.groups + g_begin) * kBlockBytes;
+  // record of (block j, group gi) of mine: rec0 + (j * groups + gi) * rec_bytes
+  const uint32_t rec_bytes = static_cast<uint32_t>(p.rec_bytes);
+  const uint8_t *rec0 = p.packed + p.rec_off + (static_cast<size_t>(p.part_block_begin[part] + cb_begin) * p.groups + g_begin) * rec_bytes;
 
   DecRotMeta rm;
   const int nq = p.M > 4 ? (p.M + 3) >> 2 : 1, ntasks = ng * nq;   // rotation tasks: row blocks of 4 for M > 4
@@ -253,8 +255,8 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
     for (int r = 0; r < nrounds; ++r) {
       if (it > 0) mbar_wait(bar_wempty + 8 * st, (it - 1) & 1);
       if (elect_one()) {
-        mbar_arrive_expect_tx(bar_wfull + 8 * st, kBlockBytes);
-        bulk_g2s(smem0 + st * kDecStage, rec0 + (static_cast<size_t>(j) * p.groups + gi) * kBlockBytes, kBlockBytes, bar_wfull + 8 * st, pol);
+        mbar_arrive_expect_tx(bar_wfull + 8 * st, rec_bytes);
+        bulk_g2s(smem0 + st * rec_bytes, rec0 + (static_cast<size_t>(j) * p.groups + gi) * rec_bytes, rec_bytes, bar_wfull + 8 * st, pol);
         if (p.trace && blockIdx.x == 0 && r < 100) g_dec_trace[kDecTraceCtas * kDecTraceSlots + 3 * r] = clock64() - t_entry;
       }
       __syncwarp();
@@ -333,15 +335,19 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
     uint32_t par = 0, epi = 0;
     const uint32_t ta = tmem + lane_base + e * 64;
     const uint32_t col_off = (L128 >> 4) * 1024 + (L128 & 15) * 16;   // my 16-byte slots inside a record's weights
+    const bool q2 = p.q2 != 0;
+    const uint32_t zero_off = q2 ? block_zero_off(2) : block_zero_off(1);
     bool first = true;
 #pragma unroll 1
     for (int r = e; r < nrounds; r += SETS) {
       mbar_wait(bar_wfull + 8 * st, par);
       if (first) { DEC_TRACE(5); first = false; }
       if (p.trace && q == 0 && lane == 0 && blockIdx.x == 0 && r < 100) g_dec_trace[kDecTraceCtas * kDecTraceSlots + 3 * r + 1] = clock64() - t_entry;
-      const uint32_t rec = smem0 + st * kDecStage;
+      const uint32_t rec = smem0 + st * rec_bytes;
       RowDequant<T> dq;
-      dq.prep(lds16(rec + kBlockScaleOff + 2 * L128), lds8(rec + kBlockZeroOff + L128));
+      dq.prep(lds16(rec + kBlockScaleOff + 2 * L128), lds8(rec + zero_off + L128));
+      uint32_t s_hi = 0, z_hi = 0;   // group_size 64: channels 64..127 of the record have their own scale / zero
+      if (q2) { s_hi = lds16(rec + kBlockScaleOff + 256 + 2 * L128); z_hi = lds8(rec + zero_off + 128 + L128); }
       if (use > 0) mbar_wait(bar_afree + 8 * e, (use - 1) & 1);  // the MMAs of my previous round have drained my A buffer
       tc_fence_after();
       const uint32_t wbase = rec + col_off;
@@ -349,6 +355,7 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 2), 1) decode_kernel(const De
       for (int c = 0; c < 4; ++c) {
         const uint4 w4 = lds128(wbase + c * 256);
         uint32_t regs[16];
+        if (c == 2 && q2) dq.prep(s_hi, z_hi);
         dq.word(w4.x, regs + 0);
         dq.word(w4.y, regs + 4);
         dq.word(w4.z, regs + 8);
@@ -506,13 +513,13 @@ static bool dec_split_ranges(const Layout &L, int ranges, DecPlan &plan) {
 
 struct DecSmem { int xb_off, rot_off, recv_off, bar_off, nstages, rot_warps, total; };
 
-static bool dec_carve_with(const DecPlan &plan, int M, int rot_bytes, int sets, int rot_warps, DecSmem &s) {
+static bool dec_carve_with(const DecPlan &plan, int M, int rot_bytes, int sets, int rot_warps, int stage_bytes, DecSmem &s) {
   const int xb_bytes = plan.ng_max * kDecN * 256;
   const int rot_total = (rot_warps * rot_bytes + 127) / 128 * 128;
   const int recv = plan.c > 1 ? ((plan.nj_max + plan.c - 1) / plan.c) * plan.c * M * 512 : 0;
   const int bar_bytes = 16 * kDecMaxStages + 256;
   const int fixed = xb_bytes + rot_total + recv + bar_bytes + 128;
-  int nst = (kDecSmemLimit - fixed) / kDecStage;
+  int nst = (kDecSmemLimit - fixed) / stage_bytes;
   if (nst > kDecMaxStages) nst = kDecMaxStages;
   const int want = dec_knobs().stages;
   if (want >= sets && want < nst) nst = want;
@@ -520,7 +527,7 @@ static bool dec_carve_with(const DecPlan &plan, int M, int rot_bytes, int sets, 
   if (nst < sets) return false;
   s.nstages = nst;
   s.rot_warps = rot_warps;
-  s.xb_off = (nst * kDecStage + 127) / 128 * 128;
+  s.xb_off = (nst * stage_bytes + 127) / 128 * 128;
   s.rot_off = s.xb_off + xb_bytes;
   s.recv_off = s.rot_off + rot_total;
   s.bar_off = s.recv_off + (recv + 127) / 128 * 128;
@@ -529,11 +536,11 @@ static bool dec_carve_with(const DecPlan &plan, int M, int rot_bytes, int sets, 
 }
 
 // every group gets its own rotating warp when the tiles fit; otherwise fewer warps take several groups each
-static bool dec_carve(const DecPlan &plan, int M, int rot_bytes, int sets, DecSmem &s) {
+static bool dec_carve(const DecPlan &plan, int M, int rot_bytes, int sets, int stage_bytes, DecSmem &s) {
   const int ntasks = plan.ng_max * (M > 4 ? (M + 3) / 4 : 1);
   int rw = ntasks < 4 * sets ? ntasks : 4 * sets;
   for (;;) {
-    if (dec_carve_with(plan, M, rot_bytes, sets, rw, s)) return true;
+    if (dec_carve_with(plan, M, rot_bytes, sets, rw, stage_bytes, s)) return true;
     if (rw <= 2) return false;
     rw = rw > 8 ? 8 : rw / 2;
   }
@@ -580,12 +587,12 @@ static bool dec_choose_plan(const Layout &L, int M, int rot_bytes, int sets, int
     plan.ng_max = (L.groups + c - 1) / c;
     if (!dec_split_ranges(L, sms / c, plan)) continue;
     DecSmem s;
-    if (!dec_carve(plan, M, rot_bytes, sets, s)) continue;
+    if (!dec_carve(plan, M, rot_bytes, sets, L.rec_bytes, s)) continue;
     const int res = resident(c, s.total);
     if (res < L.n_parts) continue;
     if (res < plan.ranges) {
       if (!dec_split_ranges(L, res, plan)) continue;
-      if (!dec_carve(plan, M, rot_bytes, sets, s)) continue;
+      if (!dec_carve(plan, M, rot_bytes, sets, L.rec_bytes, s)) continue;
     }
     plan.grid = plan.ranges * c;
     // critical path in rounds: main loop of the busiest CTA + rotation passes + a small charge per doubling of the cluster
@@ -624,14 +631,14 @@ static int launch_decode(DecParams &p, const Layout &L, int sms, cudaStream_t st
   // the plan (cluster size, block ranges, shared-memory carve-up) depends on the shape, M and the device only: searched once
   // (the search asks the occupancy API and sets the function attribute), then looked up -- an eager launch is a map lookup
   struct Key {
-    int K, N, krot, n_parts, M, dev, parts[PARO_MAX_PARTS];
+    int K, N, krot, n_parts, M, dev, qhalves, parts[PARO_MAX_PARTS];
     bool operator<(const Key &o) const { return memcmp(this, &o, sizeof(Key)) < 0; }
   };
   static std::mutex mu;
   static std::map<Key, DecCached> cache;
   Key key;
   memset(&key, 0, sizeof(key));
-  key.K = L.K; key.N = L.N; key.krot = L.krot; key.n_parts = L.n_parts; key.M = p.M;
+  key.K = L.K; key.N = L.N; key.krot = L.krot; key.n_parts = L.n_parts; key.M = p.M; key.qhalves = L.qhalves;
   if (cudaGetDevice(&key.dev) != cudaSuccess) key.dev = 0;
   for (int i = 0; i < L.n_parts; ++i) key.parts[i] = L.part_col_begin[i + 1] - L.part_col_begin[i];
   DecCached c;
@@ -736,6 +743,7 @@ int decode_forward(const paro_linear_shape &s, const Layout &L, const void *pack
   p.x_part_stride = prerot ? static_cast<long long>(kDecN) * L.K : 0;
   p.M = static_cast<int>(M); p.K = L.K; p.N = L.N;
   p.n_parts = L.n_parts; p.groups = L.groups; p.krot = L.krot;
+  p.rec_bytes = L.rec_bytes; p.q2 = L.qhalves == 2;
   p.rot_bytes = dec_rot_bytes(M);
   p.trace = dec_knobs().trace;
   for (int i = 0; i <= PARO_MAX_PARTS; ++i) {

@@ -29,7 +29,7 @@ constexpr int kGemmTmemCols = 512;
 constexpr int kWStages = 8;   // rounds of weights in flight (8 KB each); a multiple of kGemmSets
 constexpr int kBStages = 4;   // k64 stages of x_rot in flight (NT * 128 bytes each)
 constexpr int kABufs = kGemmSets;   // one A buffer (64 TMEM columns) per dequant set; D takes the other 256 columns
-constexpr int kWStage = kBlockBytes;   // one (block, group) record per ring stage
+constexpr int kWStage = kBlockBytesMax;   // one (block, group) record per ring stage (8576 bytes, 8960 with group_size 64)
 
 struct GemmParams {
   const uint8_t *packed;
@@ -38,6 +38,7 @@ struct GemmParams {
   const void *bias;
   int M, K, N, NT, n_blocks, tok_blocks;
   int n_parts, groups;
+  int rec_bytes, q2;       // record size; q2: group_size 64, two scale / zero sets per record (paro_layout.h)
   int part_col_begin[PARO_MAX_PARTS + 1];
   int part_block_begin[PARO_MAX_PARTS + 1];
   long long rec_off, xr_part_stride;
@@ -82,13 +83,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const GemmPara
     // ================= weight producer: independent of the pre-pass; every 128-column block is re-read by
     // all token blocks, so the units stay under the normal L2 policy (no evict-first here)
     if (lane == 0) {
-      const uint8_t *rec = p.packed + p.rec_off + static_cast<size_t>(block) * p.groups * kBlockBytes;
+      const uint32_t rec_bytes = static_cast<uint32_t>(p.rec_bytes);
+      const uint8_t *rec = p.packed + p.rec_off + static_cast<size_t>(block) * p.groups * rec_bytes;
       for (int r = 0; r < rounds; ++r) {
         const int ws = r % kWStages, wit = r / kWStages;
         if (wit > 0) mbar_wait(bar_wempty + 8 * ws, (wit - 1) & 1);
-        mbar_arrive_expect_tx(bar_wfull + 8 * ws, kBlockBytes);
+        mbar_arrive_expect_tx(bar_wfull + 8 * ws, rec_bytes);
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(w_ring + ws * kWStage), "l"(rec + static_cast<size_t>(r) * kBlockBytes), "r"(kBlockBytes), "r"(bar_wfull + 8 * ws)
+                     ::"r"(w_ring + ws * kWStage), "l"(rec + static_cast<size_t>(r) * rec_bytes), "r"(rec_bytes), "r"(bar_wfull + 8 * ws)
                      : "memory");
       }
     }
@@ -151,13 +153,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const GemmPara
     // A buffers shared between sets, a fast set could ask for a phase two ahead of the barrier and the parity test
     // passes on the stale phase (seen as a hang / wrong results once the weight stream stopped pacing the workers).
     const uint32_t ta = tmem + lane_base + e * 64;
+    const bool q2 = p.q2 != 0;
+    const uint32_t zero_off = q2 ? block_zero_off(2) : block_zero_off(1);
     int use = 0;
     for (int r = e; r < rounds; r += kGemmSets) {
       const int ws = r % kWStages;
       mbar_wait(bar_wfull + 8 * ws, (r / kWStages) & 1);
       const uint32_t rec = w_ring + ws * kWStage;
       RowDequant<T> dq;
-      dq.prep(lds16(rec + kBlockScaleOff + 2 * L128), lds8(rec + kBlockZeroOff + L128));   // zero-filled past the partition's end
+      dq.prep(lds16(rec + kBlockScaleOff + 2 * L128), lds8(rec + zero_off + L128));   // zero-filled past the partition's end
+      uint32_t s_hi = 0, z_hi = 0;   // group_size 64: channels 64..127 of the record have their own scale / zero
+      if (q2) { s_hi = lds16(rec + kBlockScaleOff + 256 + 2 * L128); z_hi = lds8(rec + zero_off + 128 + L128); }
       if (use > 0) mbar_wait(bar_afree + 8 * e, (use - 1) & 1);
       tc_fence_after();
       const uint32_t wbase = rec + col_off;
@@ -165,6 +171,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const GemmPara
       for (int c = 0; c < 4; ++c) {
         const uint4 w4 = lds128(wbase + c * 256);
         uint32_t regs[16];
+        if (c == 2 && q2) dq.prep(s_hi, z_hi);
         dq.word(w4.x, regs + 0);
         dq.word(w4.y, regs + 4);
         dq.word(w4.z, regs + 8);
@@ -293,6 +300,7 @@ int gemm_forward(const paro_linear_shape &s, const Layout &L, const void *packed
   p.n_blocks = L.blocks_total;
   p.tok_blocks = static_cast<int>(m_pad / NT);
   p.n_parts = L.n_parts; p.groups = L.groups;
+  p.rec_bytes = L.rec_bytes; p.q2 = L.qhalves == 2;
   for (int i = 0; i <= PARO_MAX_PARTS; ++i) {
     p.part_col_begin[i] = L.part_col_begin[i];
     p.part_block_begin[i] = L.part_block_begin[i];

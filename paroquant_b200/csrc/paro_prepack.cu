@@ -36,9 +36,12 @@ __global__ void prepack_meta_kernel(Layout L, const int16_t *__restrict__ pairs,
   const int part = idx / (static_cast<int64_t>(kGroup) * L.groups);
   uint8_t *blk = packed + L.meta_offset(part, gk);
   const int K = L.K;
+  // group_size 64: indices are local to the 64-channel group; the second group of the record moves up by 64, so the two
+  // rotations become ONE 128-channel rotation of identical arithmetic (theta: 2 x 32 consecutive values = the same 64)
+  const int16_t lift = (L.qhalves == 2 && c >= 64) ? 64 : 0, imask = L.qhalves == 2 ? 0x3F : 0x7F;
   for (int r = 0; r < L.krot; ++r) {
-    const int16_t v = pairs[(static_cast<int64_t>(part) * L.krot + r) * K + gk * kGroup + c];
-    blk[r * 128 + c] = static_cast<uint8_t>(v & 0x7F);
+    const int16_t v = static_cast<int16_t>((pairs[(static_cast<int64_t>(part) * L.krot + r) * K + gk * kGroup + c] & imask) + lift);
+    blk[r * 128 + c] = static_cast<uint8_t>(v);
     if (c < 64) {
       const int64_t ti = (static_cast<int64_t>(part) * L.krot + r) * (K / 2) + gk * 64 + c;
       reinterpret_cast<uint16_t *>(blk + L.krot * 128)[r * 64 + c] = cast_to_T_bits(theta, ti, theta_dtype, L.dtype);
@@ -52,7 +55,8 @@ __global__ void prepack_meta_kernel(Layout L, const int16_t *__restrict__ pairs,
   uint16_t *rt = reinterpret_cast<uint16_t *>(raw + static_cast<size_t>(L.krot) * K * 2);
   uint16_t *rs = reinterpret_cast<uint16_t *>(raw + static_cast<size_t>(L.krot) * K * 3);
   for (int r = 0; r < L.krot; ++r) {
-    rp[static_cast<int64_t>(r) * K + gk * kGroup + c] = pairs[(static_cast<int64_t>(part) * L.krot + r) * K + gk * kGroup + c];
+    rp[static_cast<int64_t>(r) * K + gk * kGroup + c] =
+        static_cast<int16_t>(pairs[(static_cast<int64_t>(part) * L.krot + r) * K + gk * kGroup + c] + lift);   // the pre-pass always runs with groups of 128
     if (c < 64)
       rt[static_cast<int64_t>(r) * (K / 2) + gk * 64 + c] =
           cast_to_T_bits(theta, (static_cast<int64_t>(part) * L.krot + r) * (K / 2) + gk * 64 + c, theta_dtype, L.dtype);
@@ -88,29 +92,31 @@ __global__ void prepack_weight_kernel(Layout L, const int32_t *__restrict__ qwei
 #pragma unroll
     for (int e = 0; e < 8; ++e) w |= awq_nibble(qweight, kb + e, n, nc8) << kNibblePos[e];
   }
-  reinterpret_cast<uint32_t *>(packed + L.rec_off + rec * kBlockBytes)[idx & 2047] = w;
+  reinterpret_cast<uint32_t *>(packed + L.rec_off + rec * L.rec_bytes)[idx & 2047] = w;
 }
 
 __global__ void prepack_qparam_kernel(Layout L, const int32_t *__restrict__ qzeros, const void *__restrict__ scales,
                                       int scales_dtype, uint8_t *__restrict__ packed) {
-  // one thread per (record, column of the block)
+  // one thread per (record, quantisation group h of the record, column of the block)
   const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  const int64_t total = static_cast<int64_t>(L.blocks_total) * L.groups * kBlockN;
+  const int64_t total = static_cast<int64_t>(L.blocks_total) * L.groups * L.qhalves * kBlockN;
   if (idx >= total) return;
   const int col = idx & 127;
-  const int64_t rec = idx >> 7;
+  const int h = static_cast<int>((idx >> 7) % L.qhalves);
+  const int64_t rec = (idx >> 7) / L.qhalves;
   const int block = static_cast<int>(rec / L.groups), g = static_cast<int>(rec % L.groups);
   const int part = block_part(L, block);
   const int n = L.part_col_begin[part] + (block - L.part_block_begin[part]) * kBlockN + col;
   uint16_t s = 0;
   uint8_t z = 0;
   if (n < L.part_col_begin[part + 1]) {
-    s = cast_to_T_bits(scales, static_cast<int64_t>(g) * L.N + n, scales_dtype, L.dtype);
-    z = static_cast<uint8_t>(awq_nibble(qzeros, g, n, L.N / 8));
+    const int64_t qg = static_cast<int64_t>(g) * L.qhalves + h;   // row of the checkpoint's scales / qzeros
+    s = cast_to_T_bits(scales, qg * L.N + n, scales_dtype, L.dtype);
+    z = static_cast<uint8_t>(awq_nibble(qzeros, qg, n, L.N / 8));
   }
-  uint8_t *rb = packed + L.rec_off + rec * kBlockBytes;
-  reinterpret_cast<uint16_t *>(rb + kBlockScaleOff)[col] = s;
-  rb[kBlockZeroOff + col] = z;
+  uint8_t *rb = packed + L.rec_off + rec * L.rec_bytes;
+  reinterpret_cast<uint16_t *>(rb + kBlockScaleOff)[h * 128 + col] = s;
+  rb[block_zero_off(L.qhalves) + h * 128 + col] = z;
 }
 
 // Inverse, for tests: dense W[k][n] = T((q - z) * s_T), the exact operand the GEMM consumes.
@@ -130,8 +136,9 @@ __global__ void unpack_dense_kernel(Layout L, const uint8_t *__restrict__ packed
   const uint8_t *rb = packed + L.record_offset(block, g);
   const uint32_t w = reinterpret_cast<const uint32_t *>(rb)[t * 256 + c * 64 + row * 4 + j];
   const int q = (w >> kNibblePos[e]) & 0xF;
-  const int z = rb[kBlockZeroOff + col];
-  const T s = reinterpret_cast<const T *>(rb + kBlockScaleOff)[col];
+  const int h = L.qhalves == 2 ? kl >> 6 : 0;
+  const int z = rb[block_zero_off(L.qhalves) + h * 128 + col];
+  const T s = reinterpret_cast<const T *>(rb + kBlockScaleOff)[h * 128 + col];
   // (q - z) is exact in T; one rounding in the product, like the fused kernels
   W[idx] = Traits<T>::from_float(static_cast<float>(q - z) * Traits<T>::to_float(s));
 }
@@ -151,7 +158,7 @@ int prepack_launch(const paro_linear_shape &s, const Layout &L, const int32_t *q
     prepack_weight_kernel<<<static_cast<unsigned>((total + B - 1) / B), B, 0, stream>>>(L, qweight, out);
   }
   {
-    const int64_t total = static_cast<int64_t>(L.blocks_total) * L.groups * kBlockN;
+    const int64_t total = static_cast<int64_t>(L.blocks_total) * L.groups * L.qhalves * kBlockN;
     prepack_qparam_kernel<<<static_cast<unsigned>((total + B - 1) / B), B, 0, stream>>>(L, qzeros, scales, scales_dtype, out);
   }
   PARO_CUDA_OK(cudaGetLastError());

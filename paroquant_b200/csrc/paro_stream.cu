@@ -56,7 +56,7 @@ constexpr int kStmTmemCols = 512;
 constexpr uint32_t kStmDCol0 = 64 * kStmABufs;   // 448; D buffers take the last 64 columns
 constexpr int kStmN = 16;                        // MMA N (M_mma = 128 needs N % 16 == 0)
 constexpr int kStmSmemLimit = 227 * 1024;
-constexpr int kStmStage = kBlockBytes;
+// ring stage = one record: StreamParams::stage_bytes = the largest record of the chain's steps (8576, or 8960 with group_size 64)
 constexpr int kStmBarBytes = 16 * kStmMaxStages + 320;   // barriers (224 bytes after the ring's) + 16 rstd floats
 constexpr int kStmMiscBytes = 4096;              // epilogue scratch: per warp, 64 segments x {block, global block, contributors, my slot | reducer}
 
@@ -89,6 +89,7 @@ struct StepDesc {
   int stats_in_blocks;
   int x_ld;
   int K, N, n_parts, groups, krot, meta_group_bytes;
+  int rec_bytes, q2;        // record size; q2: group_size 64, two scale / zero sets per record (paro_layout.h)
   int c, T, max_slots, blocks_total;
   long long meta_off, rec_off;
   int part_col_begin[PARO_MAX_PARTS + 1];
@@ -102,6 +103,7 @@ struct StreamParams {
   int rot_bytes, rot_warps;
   int xb_off, rot_off, misc_off, bar_off;
   int trace, inflight;        // inflight: bulk copies outstanding per SM
+  int stage_bytes;            // ring stage stride
   uint32_t *sync;             // [0] epoch (tag of a launch = epoch + 1), [1] CTAs done
   StepDesc steps[kStmMaxSteps];
 };
@@ -504,7 +506,8 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 6), 1) stream_kernel(const __
       const StepDesc &S = p.steps[i];
       const StepGeom g = step_geom(S, cta);
       if (!g.active) continue;
-      const uint8_t *rec_part = S.packed + S.rec_off + (static_cast<size_t>(S.part_block_begin[g.part]) * S.groups + g.g_begin) * kBlockBytes;
+      const uint32_t rec_bytes = static_cast<uint32_t>(S.rec_bytes);
+      const uint8_t *rec_part = S.packed + S.rec_off + (static_cast<size_t>(S.part_block_begin[g.part]) * S.groups + g.g_begin) * rec_bytes;
       const SegWalk sw = seg_walk(g);
 #pragma unroll 1
       for (int k = 0; k < sw.nseg; ++k) {
@@ -518,8 +521,8 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 6), 1) stream_kernel(const __
           // at most `inflight` records outstanding per SM (the stage of copy n - inflight has not been reused yet)
           if (issued >= static_cast<uint32_t>(p.inflight)) mbar_wait(bar_wfull + 8 * lag_st, lag_it & 1);
           if (elect_one()) {
-            mbar_arrive_expect_tx(bar_wfull + 8 * st, kBlockBytes);
-            bulk_g2s(smem0 + st * kStmStage, rec_part + (static_cast<size_t>(jb) * S.groups + gi) * kBlockBytes, kBlockBytes, bar_wfull + 8 * st, pol);
+            mbar_arrive_expect_tx(bar_wfull + 8 * st, rec_bytes);
+            bulk_g2s(smem0 + st * p.stage_bytes, rec_part + (static_cast<size_t>(jb) * S.groups + gi) * rec_bytes, rec_bytes, bar_wfull + 8 * st, pol);
           }
           __syncwarp();
           if (++st == NS) { st = 0; ++it; }
@@ -835,14 +838,18 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 6), 1) stream_kernel(const __
 
       const uint32_t nr = static_cast<uint32_t>(g.r1 - g.r0);
       const uint32_t rr_end = rr_base + nr;
+      const bool q2 = S.q2 != 0;
+      const uint32_t zero_off = q2 ? block_zero_off(2) : block_zero_off(1);
       bool first = true;
 #pragma unroll 1
       for (; rr < rr_end; rr += SETS) {
         mbar_wait(bar_wfull + 8 * st, par);
         if (first) { if (wi == 0) STM_TRACE(i, 4); first = false; }
-        const uint32_t rec = smem0 + st * kStmStage;
+        const uint32_t rec = smem0 + st * p.stage_bytes;
         RowDequant<T> dq;
-        dq.prep(lds16(rec + kBlockScaleOff + 2 * L128), lds8(rec + kBlockZeroOff + L128));
+        dq.prep(lds16(rec + kBlockScaleOff + 2 * L128), lds8(rec + zero_off + L128));
+        uint32_t s_hi = 0, z_hi = 0;   // group_size 64: channels 64..127 of the record have their own scale / zero
+        if (q2) { s_hi = lds16(rec + kBlockScaleOff + 256 + 2 * L128); z_hi = lds8(rec + zero_off + 128 + L128); }
         const uint32_t wbase = rec + col_off;
         const uint32_t ta = tmem + lane_base + a * 64;
         // the first chunk is dequantised before the wait for the A buffer (it only needs registers)
@@ -859,6 +866,7 @@ __global__ void __launch_bounds__(32 * (4 * SETS + 6), 1) stream_kernel(const __
         for (int c = 1; c < 4; ++c) {
           w4 = lds128(wbase + c * 256);
           uint32_t r2[16];
+          if (c == 2 && q2) dq.prep(s_hi, z_hi);
           dq.word(w4.x, r2 + 0);
           dq.word(w4.y, r2 + 4);
           dq.word(w4.z, r2 + 8);
@@ -993,7 +1001,7 @@ static bool stm_choose_plan(const Layout &L, int M, int sets, int ctas, int forc
     if (!stm_deal_members(L, pl.T, pl.part_cta_begin)) continue;
     pl.ng_max = (L.groups + c - 1) / c;
     const int xb_bytes = pl.ng_max * NR * 256;
-    const int nst_room = (kStmSmemLimit - xb_bytes - 4 * sets * kGroup * 2 * stm_rot_rows(M) - kStmBarBytes - kStmMiscBytes - 256) / kStmStage / sets * sets;
+    const int nst_room = (kStmSmemLimit - xb_bytes - 4 * sets * kGroup * 2 * stm_rot_rows(M) - kStmBarBytes - kStmMiscBytes - 256) / kBlockBytesMax / sets * sets;
     if (nst_room < sets) continue;
     pl.max_rounds = 0;
     pl.max_slots = 1;
@@ -1115,7 +1123,7 @@ static int stm_launch(StreamParams &p, int max_ng, int ctas, cudaStream_t stream
   for (;;) {
     const int rot_total = (rw * p.rot_bytes + 127) / 128 * 128;
     const int fixed = xb_bytes + rot_total + kStmMiscBytes + kStmBarBytes + 128;
-    int nst = (kStmSmemLimit - fixed) / kStmStage;
+    int nst = (kStmSmemLimit - fixed) / p.stage_bytes;
     if (nst > kStmMaxStages) nst = kStmMaxStages;
     if (kn.stages >= SETS && kn.stages < nst) nst = kn.stages;
     nst = nst / SETS * SETS;
@@ -1123,7 +1131,7 @@ static int stm_launch(StreamParams &p, int max_ng, int ctas, cudaStream_t stream
       p.nstages = nst;
       p.inflight = kn.inflight < 1 ? 1 : kn.inflight > nst - 1 ? nst - 1 : kn.inflight;
       p.rot_warps = rw;
-      p.xb_off = (nst * kStmStage + 127) / 128 * 128;
+      p.xb_off = (nst * p.stage_bytes + 127) / 128 * 128;
       p.rot_off = p.xb_off + xb_bytes;
       p.misc_off = p.rot_off + rot_total;
       p.bar_off = p.misc_off + kStmMiscBytes;
@@ -1218,6 +1226,8 @@ int stream_forward(const HostStep *steps, int n, int64_t M, void *workspace, siz
     S.c = pl.c; S.T = pl.T; S.max_slots = pl.max_slots; S.blocks_total = L.blocks_total;
     S.meta_off = static_cast<long long>(L.meta_off);
     S.rec_off = static_cast<long long>(L.rec_off);
+    S.rec_bytes = L.rec_bytes; S.q2 = L.qhalves == 2;
+    if (L.rec_bytes > p.stage_bytes) p.stage_bytes = L.rec_bytes;
     for (int k = 0; k <= PARO_MAX_PARTS; ++k) {
       S.part_col_begin[k] = L.part_col_begin[k];
       S.part_block_begin[k] = L.part_block_begin[k];

@@ -43,8 +43,11 @@ def test_size_queries_and_shape_errors():
     # a partition that is not a whole number of 128-column blocks is padded to one
     s2 = _cabi.make_shape(256, [272, 16], 128, 8, torch.float16)
     assert _cabi.packed_bytes(s2) == (3 + 1) * 2 * 8576 + 2 * 2 * 2304 + raw(256, 2)
+    # group_size 64: a record still covers 128 channels and carries two scale / zero sets (8960 bytes)
+    s64 = _cabi.make_shape(4096, [4096], 64, 8, torch.bfloat16)
+    assert _cabi.packed_bytes(s64) == 32 * 32 * 8960 + 32 * 2304 + raw(4096, 1)
     for bad, msg in ((dict(in_features=4000), "multiple of 128"), (dict(part_sizes=[100]), "multiple of 16"),
-                     (dict(group_size=64), "group_size"), (dict(krot=17), "krot")):
+                     (dict(group_size=32), "group_size"), (dict(krot=17), "krot")):
         kw = dict(in_features=4096, part_sizes=[4096], group_size=128, krot=8, dtype=torch.bfloat16)
         kw.update(bad)
         with pytest.raises(RuntimeError, match=msg):

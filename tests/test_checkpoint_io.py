@@ -80,7 +80,7 @@ def test_loader_errors(tmp_path):
     with pytest.raises(ValueError, match="expected 'paroquant'"):
         cio.load_paro_checkpoint(tmp_path)
     (tmp_path / "config.json").write_text(json.dumps({"quantization_config": {"quant_method": "paroquant", "bits": 3, "group_size": 128, "krot": 8}}))
-    with pytest.raises(ValueError, match="INT4 group-128 only"):
+    with pytest.raises(ValueError, match="INT4 with group_size 64 or 128 only"):
         cio.load_paro_checkpoint(tmp_path)
     (tmp_path / "config.json").write_text(json.dumps({"quantization_config": {"quant_method": "paroquant", "bits": 4, "group_size": 128, "krot": 4}}))
     with pytest.raises(ValueError, match="buffer shapes do not match"):

@@ -9,11 +9,11 @@ import torch
 from paroquant_b200 import _cabi
 
 SMEM_LIMIT = 227 * 1024
-REC = 8576
+REC = {128: 8576, 64: 8960}   # record = ring stage: group_size 64 carries two scale / zero sets (paro_layout.h)
 
 
-def plan(K, parts, M, sets=5, sms=148, resident=(148, 74, 33, 16)):
-    shape = _cabi.make_shape(K, parts, 128, 8, torch.bfloat16)
+def plan(K, parts, M, sets=5, sms=148, resident=(148, 74, 33, 16), group=128):
+    shape = _cabi.make_shape(K, parts, group, 8, torch.bfloat16)
     out = (ctypes.c_int32 * 20)()
     res = (ctypes.c_int32 * 4)(*resident)
     lib = _cabi.lib()
@@ -33,9 +33,9 @@ SHAPES = [(4096, [4096]), (4096, [4096, 1024, 1024]), (4096, [14336, 14336]), (1
 
 @pytest.mark.parametrize("K,parts", SHAPES)
 @pytest.mark.parametrize("M", [1, 3, 4, 8, 9, 16])
-@pytest.mark.parametrize("sets", [5, 6])
-def test_plan_covers_the_layer_once_and_fits(K, parts, M, sets):
-    p, prb = plan(K, parts, M, sets)
+@pytest.mark.parametrize("sets,group", [(5, 128), (6, 128), (5, 64)])
+def test_plan_covers_the_layer_once_and_fits(K, parts, M, sets, group):
+    p, prb = plan(K, parts, M, sets, group=group)
     c, groups = p["c"], K // 128
     blocks = [(n + 127) // 128 for n in parts]
     assert c in (1, 2, 4, 8) and c <= groups
@@ -66,7 +66,7 @@ def test_plan_covers_the_layer_once_and_fits(K, parts, M, sets):
     ntasks = p["ng_max"] * ((M + 3) // 4 if M > 4 else 1)
     assert 1 <= p["rot_warps"] <= min(4 * sets, ntasks)
     assert p["smem"] <= SMEM_LIMIT
-    assert p["xb_off"] >= p["nstages"] * REC and p["xb_off"] % 128 == 0
+    assert p["xb_off"] >= p["nstages"] * REC[group] and p["xb_off"] % 128 == 0
     rot_bytes = 256 * (1 if M == 1 else 2 if M == 2 else 4)
     recv = ((p["nj_max"] + c - 1) // c) * c * M * 512 if c > 1 else 0
     assert p["recv_off"] >= p["xb_off"] + p["ng_max"] * 4096 + p["rot_warps"] * rot_bytes    # B operand, then the rotation tiles

@@ -196,3 +196,26 @@ def test_chain_argument_checks(mods):
     with pytest.raises(RuntimeError, match="alias"):
         r = torch.zeros(2, 128, dtype=torch.bfloat16, device="cuda")
         chain.ParoChain([chain.ChainStep(k, x=x, epilogue="add_residual", residual_in=r, residual_out=r)], 2)
+
+
+@pytest.mark.parametrize("M", [1, 4])
+def test_chain_mixes_group64_and_group128_steps(mods, oracle, M):
+    """A chain whose steps have different record sizes (group_size 64: two scale / zero sets per record): the ring stage is
+    sized for the largest, every step copies its own record size."""
+    chain, PK = mods
+    dt, T = "bfloat16", torch.bfloat16
+    La = make_synthetic_layer(512, [768], group_size=64, seed=301)
+    Lb = make_synthetic_layer(768, [256, 128], group_size=128, seed=302)
+    Lc = make_synthetic_layer(384, [512], group_size=64, seed=303)
+    ka, kb, kc = (PK.from_buffers(L.to("cuda"), T, check_pairs=False) for L in (La, Lb, Lc))
+    x = make_synthetic_activations(M, 512, seed=310, dtype=T).cuda()
+    ya = torch.empty(M, 768, dtype=T, device="cuda")
+    yb = torch.empty(M, 384, dtype=T, device="cuda")
+    yc = torch.empty(M, 512, dtype=T, device="cuda")
+    ch = chain.ParoChain([chain.ChainStep(ka, x=x, y=ya), chain.ChainStep(kb, y=yb), chain.ChainStep(kc, y=yc)], M)
+    ch()
+    torch.cuda.synchronize()
+    O = oracle
+    assert O.rel_err(_np(ya), O.linear(_np(x), La.numpy_dict(), dt)) < TOL
+    assert O.rel_err(_np(yb), O.linear(_np(ya), Lb.numpy_dict(), dt)) < TOL
+    assert O.rel_err(_np(yc), O.linear(_np(yb), Lc.numpy_dict(), dt)) < TOL

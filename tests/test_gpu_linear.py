@@ -271,3 +271,53 @@ def test_linear_op_is_opaque_under_torch_compile(PK):
     for M in (1, 7, 48, 300):
         x = make_synthetic_activations(M, 1024, seed=M, device="cuda")
         assert torch.equal(cf(x), f(x))
+
+
+# ---------------------------------------------------------------- group_size 64
+# The converter rotates AND quantises in groups of `group_size` (cli/convert.py:176-182) and the rotate op dispatches 64 and
+# 128 (rotation.cu:117-123).  The reference's inference call sites drop the argument (plugin.py:285, modules.py:59 rotate with
+# the default 128), so there is no reference pipeline to compare with: the oracle with group = 64 on both halves is the bar.
+@pytest.mark.parametrize("dt", ["bfloat16", "float16"])
+@pytest.mark.parametrize("K,parts", [(512, [64]), (1024, [256, 128]), (640, [48, 16, 32])])
+def test_group64_prepack_preserves_operand_bit_exact(PK, oracle, dt, K, parts):
+    L = make_synthetic_layer(K, parts, group_size=64, seed=141)
+    k = PK.from_buffers(L.to("cuda"), _TD[dt])
+    d = L.numpy_dict()
+    assert np.array_equal(k.dense_weight().float().cpu().numpy(), oracle.c_dequant(d["qweight"], d["qzeros"], d["scales"], 64, dt))
+
+
+@pytest.mark.parametrize("dt", ["bfloat16", "float16"])
+@pytest.mark.parametrize("K,parts,Ms", [
+    (512, [64], (1, 2, 5, 16, 17)),                   # cluster kernel, pre-rotated rows from 5 on, GEMM path at 17
+    (1024, [256, 128], (1, 4, 16, 48, 300)),          # merged; 48 / 300 rows: rotation pre-pass + tcgen05 GEMM
+    (640, [48, 16, 32], (3, 12)),
+    (4096, [4096], (1, 16)),
+])
+def test_group64_fused_linear_vs_oracle(PK, oracle, dt, K, parts, Ms):
+    L = make_synthetic_layer(K, parts, group_size=64, seed=143, bias=(K == 1024))
+    assert int(L.numpy_dict()["group"]) == 64
+    k = PK.from_buffers(L.to("cuda"), _TD[dt])
+    cache = {}
+    bias = None if L.bias is None else L.bias.to("cuda", _TD[dt])
+    for M in Ms:
+        x = make_synthetic_activations(M, K, seed=150 + M, dtype=_TD[dt])
+        y = k(x.cuda(), bias)
+        ref = _oracle_linear(oracle, L, x, dt, cache)
+        err = oracle.rel_err(y.float().cpu().numpy(), ref)
+        assert err < TOL, (M, err)
+        assert torch.equal(k(x.cuda(), bias), y)
+
+
+def test_group64_rotation_equals_the_standalone_op(PK):
+    """theta as drawn, unit weights are not needed: the fused kernel on a group-64 layer equals the standalone rotate op run
+    with group_size = 64 followed by a matmul on the kernel's own dequantised operand."""
+    import paroquant_b200.kernels.cuda  # noqa: F401
+    L = make_synthetic_layer(2048, [384], group_size=64, seed=147, device="cuda")
+    k = PK.from_buffers(L, torch.bfloat16)
+    W = k.dense_weight().double()
+    for M in (1, 16, 64):
+        x = make_synthetic_activations(M, 2048, seed=160 + M, device="cuda")
+        xr = torch.ops.rotation.rotate(x, L.pairs[0], L.theta[0], L.channel_scales[0], 64)
+        ref = (xr.double() @ W).float().to(torch.bfloat16).double()
+        err = ((k(x).double() - ref).norm() / ref.norm()).item()
+        assert err < 3e-4, (M, err)
