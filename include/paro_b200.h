@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PARO_ABI_VERSION 2
+#define PARO_ABI_VERSION 3
 #define PARO_MAX_PARTS 8
 
 /* element types (activations, rotation parameters, scales) */
@@ -81,6 +81,20 @@ const char *paro_last_error(void);
 int paro_rotate(const void *x, void *out, const int16_t *idx_ij, const void *theta,
                 int32_t theta_dtype, const void *scales, int32_t scales_dtype, int64_t M,
                 int32_t K, int32_t krot, int32_t group_size, int32_t dtype, paro_stream_t stream);
+
+/* Backward of paro_rotate in ONE launch -- replaces RotateTensorFunc.backward's Python walk over the rotations
+ * (kernels/cuda/autograd.py:20-61: per rotation two rotate launches, five gathers and a reduction).
+ *   y           device [M, K] of `dtype`: the forward OUTPUT;  grad_out [M, K]: dL/dy
+ *   x           device [M, K]: the forward input, read only when grad_scale != NULL
+ *   grad_x      device [M, K] of `dtype` (written);  must not alias y / grad_out
+ *   grad_theta  device [krot, K/2] fp32, ACCUMULATED into (zero it first)
+ *   grad_scale  device [K] fp32, accumulated into, or NULL (then scales may be NULL too)
+ * t and g are rounded to `dtype` after every rotation, where the reference's per-rotation
+ * launches store them; the sums over rows run in fp32 (atomics: order-dependent last bits). */
+int paro_rotate_backward(const void *y, const void *grad_out, const void *x, const int16_t *idx_ij,
+                         const void *theta, int32_t theta_dtype, const void *scales, int32_t scales_dtype,
+                         void *grad_x, float *grad_theta, float *grad_scale, int64_t M, int32_t K,
+                         int32_t krot, int32_t group_size, int32_t dtype, paro_stream_t stream);
 
 /* Size in bytes of the kernel-layout buffer paro_prepack fills (0 on invalid shape). */
 size_t paro_packed_bytes(const paro_linear_shape *shape);

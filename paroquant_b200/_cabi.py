@@ -49,7 +49,7 @@ class ParoChainStep(ctypes.Structure):
     ]
 
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 CHAIN_MAX_STEPS = 6
 XOP_NONE, XOP_SILU_MUL, XOP_RMSNORM = 0, 1, 2
 EPI_STORE, EPI_ADD_RESIDUAL = 0, 1
@@ -73,6 +73,8 @@ def lib() -> ctypes.CDLL:
         L.paro_last_launch_count.restype = ctypes.c_int
         L.paro_rotate.restype = ctypes.c_int
         L.paro_rotate.argtypes = [vp, vp, vp, vp, i32, vp, i32, i64, i32, i32, i32, i32, vp]
+        L.paro_rotate_backward.restype = ctypes.c_int
+        L.paro_rotate_backward.argtypes = [vp, vp, vp, vp, vp, i32, vp, i32, vp, vp, vp, i64, i32, i32, i32, i32, vp]
         L.paro_packed_bytes.restype = sz
         L.paro_packed_bytes.argtypes = [shp]
         L.paro_prepack.restype = ctypes.c_int
@@ -102,7 +104,7 @@ def lib() -> ctypes.CDLL:
 
 
 EXPORTED_SYMBOLS = (
-    "paro_abi_version", "paro_last_error", "paro_last_launch_count", "paro_rotate", "paro_packed_bytes",
+    "paro_abi_version", "paro_last_error", "paro_last_launch_count", "paro_rotate", "paro_rotate_backward", "paro_packed_bytes",
     "paro_prepack", "paro_workspace_bytes", "paro_linear_forward", "paro_unpack_dense", "paro_debug_trace", "paro_debug_decode_plan",
     "paro_chain_workspace_bytes", "paro_chain_forward", "paro_debug_stream_plan", "paro_debug_stream_trace", "paro_tp_slot_bytes",
 )
@@ -175,6 +177,38 @@ def rotate(x: torch.Tensor, idx_ij: torch.Tensor, theta: torch.Tensor, scales: t
                                M, K, idx_ij.size(0), group_size, dtype_code(x.dtype), _stream(dev))
     _check(rc, "rotate")
     return out
+
+
+def rotate_backward(y: torch.Tensor, grad_out: torch.Tensor, x: torch.Tensor, idx_ij: torch.Tensor, theta: torch.Tensor,
+                    scales: torch.Tensor | None = None, group_size: int = 128):
+    """Backward of `rotate` in one launch: (grad_x, grad_theta fp32 [krot, K/2], grad_scale fp32 [K] | None).
+    Replaces the per-rotation Python walk of kernels/cuda/autograd.py:20-61."""
+    dev = _need_cuda(y, grad_out, x, idx_ij, theta, scales)
+    if idx_ij.dtype != torch.int16:
+        raise RuntimeError("idx_ij must be int16")
+    if grad_out.dtype != y.dtype or x.dtype != y.dtype:
+        raise RuntimeError("rotate_backward: y, grad_out and x must share a dtype")
+    y, grad_out, x = y.contiguous(), grad_out.contiguous(), x.contiguous()
+    idx_ij, theta = idx_ij.contiguous(), theta.contiguous()
+    has_scale = scales is not None and scales.numel() > 0
+    if has_scale:
+        scales = scales.contiguous()
+    K = y.size(-1)
+    M = y.numel() // K if K else 0
+    grad_x = torch.empty_like(y)
+    grad_theta = torch.zeros(idx_ij.size(0), K // 2, dtype=torch.float32, device=dev)
+    grad_scale = torch.zeros(K, dtype=torch.float32, device=dev) if has_scale else None
+    if M == 0:
+        dtype_code(y.dtype)
+        return grad_x, grad_theta, grad_scale
+    with torch.cuda.device(dev):
+        rc = lib().paro_rotate_backward(y.data_ptr(), grad_out.data_ptr(), x.data_ptr(), idx_ij.data_ptr(), theta.data_ptr(),
+                                        dtype_code(theta.dtype), scales.data_ptr() if has_scale else None,
+                                        dtype_code(scales.dtype) if has_scale else 0, grad_x.data_ptr(), grad_theta.data_ptr(),
+                                        grad_scale.data_ptr() if has_scale else None, M, K, idx_ij.size(0), group_size,
+                                        dtype_code(y.dtype), _stream(dev))
+    _check(rc, "rotate_backward")
+    return grad_x, grad_theta, grad_scale
 
 
 def packed_bytes(shape: ParoLinearShape) -> int:

@@ -25,6 +25,9 @@ void note_launches(int n) { g_launches += n; }
 // implemented in the kernel translation units
 int rotate_launch(const void *x, void *out, const int16_t *idx, const void *theta, int theta_dtype, const void *scales,
                   int scales_dtype, int64_t M, int K, int krot, int G, int dtype, cudaStream_t stream);
+int rotate_backward_launch(const void *y, const void *gout, const void *x, const int16_t *idx, const void *theta, int theta_dtype, const void *scales,
+                           int scales_dtype, void *grad_x, float *grad_theta, float *grad_scale, int64_t M, int K, int krot, int G, int dtype,
+                           cudaStream_t stream);
 int prepack_launch(const paro_linear_shape &s, const Layout &L, const int32_t *qweight, const int32_t *qzeros,
                    const void *scales, int scales_dtype, const int16_t *pairs, const void *theta, int theta_dtype,
                    const void *cscales, int cs_dtype, void *packed, cudaStream_t stream);
@@ -88,6 +91,24 @@ int paro_rotate(const void *x, void *out, const int16_t *idx_ij, const void *the
   if (!aligned(x, 16) || !aligned(out, 16) || !aligned(idx_ij, 4)) { set_error("rotate: x/out must be 16-byte aligned, idx_ij 4-byte"); return PARO_EINVAL; }
   return rotate_launch(x, out, idx_ij, theta, theta_dtype, scales, scales_dtype, M, K, krot, group_size, dtype,
                        static_cast<cudaStream_t>(stream));
+}
+
+int paro_rotate_backward(const void *y, const void *grad_out, const void *x, const int16_t *idx_ij, const void *theta, int32_t theta_dtype,
+                         const void *scales, int32_t scales_dtype, void *grad_x, float *grad_theta, float *grad_scale, int64_t M, int32_t K,
+                         int32_t krot, int32_t group_size, int32_t dtype, paro_stream_t stream) {
+  g_launches = 0;
+  if (!y || !grad_out || !idx_ij || !theta || !grad_x || !grad_theta) { set_error("rotate_backward: null pointer argument"); return PARO_EINVAL; }
+  if (grad_scale && (!x || !scales)) { set_error("rotate_backward: grad_scale needs x and scales"); return PARO_EINVAL; }
+  if (!valid_dtype(dtype)) { set_error("rotate supports Float, Half, and BFloat16, got dtype code %d", dtype); return PARO_EINVAL; }
+  if (!valid_dtype(theta_dtype) || (scales && !valid_dtype(scales_dtype))) { set_error("rotate_backward: bad theta/scales dtype"); return PARO_EINVAL; }
+  if (group_size != 64 && group_size != 128) { set_error("Unsupported group_size: %d; expected 64 or 128", group_size); return PARO_EUNSUPPORTED; }
+  if (K <= 0 || K % group_size) { set_error("h must be divisible by GROUP_SIZE"); return PARO_EINVAL; }
+  if (krot < 1 || krot > 16) { set_error("Unsupported KROT = %d; supported: 1..16", krot); return PARO_EUNSUPPORTED; }
+  if (M < 0) { set_error("rotate_backward: negative row count"); return PARO_EINVAL; }
+  if (grad_x == y || grad_x == grad_out) { set_error("rotate_backward: grad_x must not alias y / grad_out"); return PARO_EINVAL; }
+  if (!aligned(idx_ij, 4)) { set_error("rotate_backward: idx_ij must be 4-byte aligned"); return PARO_EINVAL; }
+  return rotate_backward_launch(y, grad_out, x, idx_ij, theta, theta_dtype, scales, scales_dtype, grad_x, grad_theta, grad_scale, M, K, krot, group_size,
+                                dtype, static_cast<cudaStream_t>(stream));
 }
 
 size_t paro_packed_bytes(const paro_linear_shape *shape) {

@@ -38,6 +38,12 @@ template <> struct Traits<__half> {
   __device__ static __forceinline__ __half2 from_floats(float a, float b) { return __floats2half2_rn(a, b); }
 };
 
+template <> struct Traits<float> {   // fp32 rotate (the optimiser's dtype): no rounding anywhere
+  static constexpr int code = PARO_F32;
+  __device__ static __forceinline__ float to_float(float v) { return v; }
+  __device__ static __forceinline__ float from_float(float v) { return v; }
+};
+
 template <> struct Traits<__nv_bfloat16> {
   using T2 = __nv_bfloat162;
   static constexpr int code = PARO_BF16;

@@ -384,6 +384,153 @@ int rotate_launch(const void *x, void *out, const int16_t *idx, const void *thet
   return PARO_EINVAL;
 }
 
+// ------------------------------------------------------------------ backward of the rotate op (training side)
+// The reference walks the krot rotations in Python, last to first: two one-rotation rotate launches (t and g with -theta), five
+// gathers and a row reduction per rotation (/root/reference/paroquant/kernels/cuda/autograd.py:20-61).  Here ONE launch does the
+// whole walk: a warp owns a group and a strided set of 4-row blocks; the stage output t (from y) and its gradient g sit in two
+// fp32 shared-memory tiles; per rotation and pair
+//     dL/dtheta += sum_rows (g_i t_j - g_j t_i)          (identity on the stage OUTPUT: dy_i/dtheta = y_j, dy_j/dtheta = -y_i)
+//     (t, g) <- Givens(-theta) (t, g)                    (orthogonal: the same update back-propagates g), rounded to T per
+//                                                         rotation exactly where the per-rotation launches rounded
+// and after the last un-rotation grad_x = g * scale, dL/dscale += x * g.  dL/dtheta and dL/dscale are accumulated per warp over
+// its row blocks in registers and added to fp32 buffers with one atomic per (rotation, pair) / channel and warp.
+template <typename T, int G>
+__global__ void __launch_bounds__(128) rotate_backward_kernel(const T *__restrict__ y, const T *__restrict__ gout, const T *__restrict__ x,
+                                                              const int16_t *__restrict__ idx, const void *__restrict__ theta, int theta_dtype,
+                                                              const void *__restrict__ scales, int scales_dtype, T *__restrict__ grad_x,
+                                                              float *__restrict__ grad_theta, float *__restrict__ grad_scale, int64_t M, int K,
+                                                              int krot, int splits) {
+  constexpr int RB = 4, CPL = G / 32, PPL = G / 64;
+  __shared__ __align__(16) float4 tile_t[4][G], tile_g[4][G];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int groups = K / G;
+  const int64_t wid = static_cast<int64_t>(blockIdx.x) * 4 + warp;   // (split, group)
+  if (wid >= static_cast<int64_t>(splits) * groups) return;
+  const int g = static_cast<int>(wid % groups), split = static_cast<int>(wid / groups);
+  const int64_t row_blocks = (M + RB - 1) / RB;
+  float4 *tt = tile_t[warp], *tg = tile_g[warp];
+  // dL/dtheta partials of this warp: [rotation][pair], each lane touches only its own pairs (shared memory, not registers: the
+  // rotation loop stays rolled -- unrolled over 16 rotations the kernel needed 160-190 registers)
+  __shared__ float acc_th[4][16][G / 2];
+  float (*acc)[G / 2] = acc_th[warp];
+  for (int r = 0; r < krot; ++r)
+#pragma unroll
+    for (int q = 0; q < PPL; ++q) acc[r][lane * PPL + q] = 0.f;
+  float acc_s[CPL], sc[CPL];
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) {
+    acc_s[c] = 0.f;
+    sc[c] = scales ? load_param_as<float>(scales, static_cast<int64_t>(g) * G + lane * CPL + c, scales_dtype) : 1.0f;   // autograd.py:55: the scale as stored
+  }
+  auto rnd = [](float v) { return Traits<T>::to_float(Traits<T>::from_float(v)); };   // the per-rotation launches store T
+  for (int64_t rb = split; rb < row_blocks; rb += splits) {
+    const int64_t row0 = rb * RB;
+    // ---- stage output and its gradient, channel-major fp32 vectors of 4 rows
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      float vt[RB], vg[RB];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const bool ok = row0 + r < M;
+        const int64_t o = (row0 + r) * K + g * G + lane * CPL + c;
+        vt[r] = ok ? Traits<T>::to_float(y[o]) : 0.f;
+        vg[r] = ok ? Traits<T>::to_float(gout[o]) : 0.f;
+      }
+      tt[rot_slot(lane * CPL + c)] = make_float4(vt[0], vt[1], vt[2], vt[3]);
+      tg[rot_slot(lane * CPL + c)] = make_float4(vg[0], vg[1], vg[2], vg[3]);
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int r = krot - 1; r >= 0; --r) {
+      {
+#pragma unroll
+        for (int q = 0; q < PPL; ++q) {
+          const int t = lane * PPL + q;
+          const int ij = *reinterpret_cast<const int *>(idx + static_cast<int64_t>(r) * K + g * G + 2 * t);
+          const int pi = rot_slot(ij & 0xFFFF), pj = rot_slot((ij >> 16) & 0xFFFF);
+          const float th = load_param_as<T>(theta, static_cast<int64_t>(r) * (K / 2) + g * (G / 2) + t, theta_dtype);
+          float sn, cs;
+          __sincosf(-th, &sn, &cs);
+          float4 ti = tt[pi], tj = tt[pj], gi = tg[pi], gj = tg[pj];
+          acc[r][t] += (gi.x * tj.x - gj.x * ti.x) + (gi.y * tj.y - gj.y * ti.y) + (gi.z * tj.z - gj.z * ti.z) + (gi.w * tj.w - gj.w * ti.w);
+          float4 ni, nj, mi, mj;
+          givens(cs, sn, ti.x, tj.x, ni.x, nj.x); givens(cs, sn, ti.y, tj.y, ni.y, nj.y);
+          givens(cs, sn, ti.z, tj.z, ni.z, nj.z); givens(cs, sn, ti.w, tj.w, ni.w, nj.w);
+          givens(cs, sn, gi.x, gj.x, mi.x, mj.x); givens(cs, sn, gi.y, gj.y, mi.y, mj.y);
+          givens(cs, sn, gi.z, gj.z, mi.z, mj.z); givens(cs, sn, gi.w, gj.w, mi.w, mj.w);
+          if constexpr (sizeof(T) == 2) {
+            ni = make_float4(rnd(ni.x), rnd(ni.y), rnd(ni.z), rnd(ni.w)); nj = make_float4(rnd(nj.x), rnd(nj.y), rnd(nj.z), rnd(nj.w));
+            mi = make_float4(rnd(mi.x), rnd(mi.y), rnd(mi.z), rnd(mi.w)); mj = make_float4(rnd(mj.x), rnd(mj.y), rnd(mj.z), rnd(mj.w));
+          }
+          tt[pi] = ni; tt[pj] = nj; tg[pi] = mi; tg[pj] = mj;
+        }
+        __syncwarp();
+      }
+    }
+    // ---- g is now dL/d(x * scale)
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const float4 gv = tg[rot_slot(lane * CPL + c)];
+      const float gr[RB] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        if (row0 + r < M) {
+          const int64_t o = (row0 + r) * K + g * G + lane * CPL + c;
+          grad_x[o] = Traits<T>::from_float(scales ? gr[r] * sc[c] : gr[r]);
+          if (grad_scale) acc_s[c] += Traits<T>::to_float(x[o]) * gr[r];
+        }
+      }
+    }
+    __syncwarp();
+  }
+  for (int r = 0; r < krot; ++r) {
+#pragma unroll
+    for (int q = 0; q < PPL; ++q) atomicAdd(grad_theta + static_cast<int64_t>(r) * (K / 2) + g * (G / 2) + lane * PPL + q, acc[r][lane * PPL + q]);
+  }
+  if (grad_scale) {
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) atomicAdd(grad_scale + static_cast<int64_t>(g) * G + lane * CPL + c, acc_s[c]);
+  }
+}
+
+template <typename T>
+static int launch_backward_T(const void *y, const void *gout, const void *x, const int16_t *idx, const void *theta, int theta_dtype, const void *scales,
+                             int scales_dtype, void *grad_x, float *grad_theta, float *grad_scale, int64_t M, int K, int krot, int G, cudaStream_t stream) {
+  const int groups = K / G;
+  const int64_t row_blocks = (M + 3) / 4;
+  // enough warps to fill the machine (148 SMs x 6 resident CTAs of 4 warps: 80 registers, 32 KB), no more splits than row blocks:
+  // every warp then walks ~row_blocks / splits blocks of its group and pays its atomics once
+  int64_t splits = (148 * 6 * 4 + groups - 1) / groups;
+  if (splits > row_blocks) splits = row_blocks;
+  if (splits < 1) splits = 1;
+  const int64_t blocks = (splits * groups + 3) / 4;
+  if (blocks > 0x7FFFFFFF) { set_error("rotate_backward: too many groups"); return PARO_EINVAL; }
+  const T *yp = static_cast<const T *>(y), *gp = static_cast<const T *>(gout), *xp = static_cast<const T *>(x);
+  T *gx = static_cast<T *>(grad_x);
+  if (G == 128)
+    rotate_backward_kernel<T, 128><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(yp, gp, xp, idx, theta, theta_dtype, scales, scales_dtype, gx, grad_theta,
+                                                                                     grad_scale, M, K, krot, static_cast<int>(splits));
+  else
+    rotate_backward_kernel<T, 64><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(yp, gp, xp, idx, theta, theta_dtype, scales, scales_dtype, gx, grad_theta,
+                                                                                    grad_scale, M, K, krot, static_cast<int>(splits));
+  PARO_CUDA_OK(cudaGetLastError());
+  note_launches(1);
+  return PARO_OK;
+}
+
+int rotate_backward_launch(const void *y, const void *gout, const void *x, const int16_t *idx, const void *theta, int theta_dtype, const void *scales,
+                           int scales_dtype, void *grad_x, float *grad_theta, float *grad_scale, int64_t M, int K, int krot, int G, int dtype,
+                           cudaStream_t stream) {
+  if (M == 0) return PARO_OK;
+  switch (dtype) {
+    case PARO_F32: return launch_backward_T<float>(y, gout, x, idx, theta, theta_dtype, scales, scales_dtype, grad_x, grad_theta, grad_scale, M, K, krot, G, stream);
+    case PARO_F16: return launch_backward_T<__half>(y, gout, x, idx, theta, theta_dtype, scales, scales_dtype, grad_x, grad_theta, grad_scale, M, K, krot, G, stream);
+    case PARO_BF16: return launch_backward_T<__nv_bfloat16>(y, gout, x, idx, theta, theta_dtype, scales, scales_dtype, grad_x, grad_theta, grad_scale, M, K, krot, G, stream);
+  }
+  set_error("rotate supports Float, Half, and BFloat16, got dtype code %d", dtype);
+  return PARO_EINVAL;
+}
+
 // Rotation pre-pass of the large-M path: the raw metadata of ONE partition, output in the B-operand tile
 // order of the tcgen05 GEMM, zero rows up to M_store (a multiple of tiled_nt).
 int rotate_tiled_launch(const void *x, void *out, const int16_t *idx, const void *theta, int theta_dtype, const void *scales,

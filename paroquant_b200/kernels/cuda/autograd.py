@@ -2,17 +2,22 @@
 
 Surface of /root/reference/paroquant/kernels/cuda/autograd.py:6-65 (`RotateTensorFunc`,
 `scaled_pairwise_rotation`) used by the offline optimiser and the checkpoint converter.
-Forward is the sm_100a kernel.  Backward walks the rotations in reverse using the identities
+Forward is the sm_100a kernel.  Backward is ONE launch (`paro_rotate_backward`,
+csrc/paro_rotate.cu) where the reference walks the rotations in Python (per rotation two rotate
+launches, five gathers and a reduction).  It uses the identities
 
     y_i =  c a + s b,   y_j = -s a + c b
     dy_i/dtheta = y_j,  dy_j/dtheta = -y_i          =>  dL/dtheta = sum_rows (G_i y_j - G_j y_i)
 
 on the stage OUTPUT (t) and its gradient (g), then un-rotates both with -theta (a Givens
-rotation is orthogonal, so the same kernel back-propagates g).
+rotation is orthogonal, so the same update back-propagates g), rounding t and g to x.dtype after
+every rotation exactly where the per-rotation launches stored them; the row sums run in fp32.
 """
 from __future__ import annotations
 
 import torch
+
+from ... import _cabi
 
 
 class RotateTensorFunc(torch.autograd.Function):
@@ -28,25 +33,13 @@ class RotateTensorFunc(torch.autograd.Function):
     def backward(ctx, grad_out):
         x, idx_ij, theta, y = ctx.saved_tensors[:4]
         scale = ctx.saved_tensors[4] if ctx.has_scale else None
-        G = ctx.group_size
-        krot, K = idx_ij.shape
-        rows = y.numel() // K
-        t = y.reshape(rows, K)
-        g = grad_out.reshape(rows, K).contiguous()
-        base = (torch.arange(K, device=idx_ij.device) // G * G).view(K // 2, 2)[:, 0]
-        grad_theta = torch.zeros_like(theta)
-        for r in reversed(range(krot)):
-            pr = idx_ij[r].view(K // 2, 2).long()
-            ci, cj = pr[:, 0] + base, pr[:, 1] + base
-            grad_theta[r] = ((g[:, ci] * t[:, cj] - g[:, cj] * t[:, ci]).sum(0)).to(theta.dtype)
-            inv = -theta[r : r + 1]
-            t = torch.ops.rotation.rotate(t, idx_ij[r : r + 1], inv, None, G)
-            g = torch.ops.rotation.rotate(g, idx_ij[r : r + 1], inv, None, G)
-        if scale is None:
-            return g.view_as(x).to(x.dtype), None, grad_theta, None, None
-        flat_scale = scale.reshape(-1)
-        grad_x = (g * flat_scale.unsqueeze(0)).view_as(x).to(x.dtype)
-        grad_scale = (x.reshape(rows, K) * g).sum(0).to(scale.dtype).view_as(scale)
+        K = idx_ij.shape[1]
+        flat_scale = None if scale is None else scale.reshape(-1)
+        gx, gth, gsc = _cabi.rotate_backward(y.reshape(-1, K), grad_out.reshape(-1, K).to(y.dtype), x.reshape(-1, K), idx_ij, theta,
+                                             flat_scale, ctx.group_size)
+        grad_x = gx.view_as(x)
+        grad_theta = gth.to(theta.dtype)
+        grad_scale = None if scale is None else gsc.to(scale.dtype).view_as(scale)
         return grad_x, None, grad_theta, grad_scale, None
 
 

@@ -141,3 +141,68 @@ def test_autograd_matches_dense_jacobian(ops):
     (scaled_pairwise_rotation(x, pr, th, sc, G) * w).sum().backward()
     for a, b in ((x.grad, gx), (th.grad, gt), (sc.grad, gs)):
         assert (a - b).norm() / b.norm() < 2e-5
+
+
+def _backward_stagewise(x, idx_ij, theta, y, grad_out, scale, G):
+    """The reference's backward structure (kernels/cuda/autograd.py:20-61): walk the rotations last to first with one-rotation
+    rotate launches on t and g; test-side restatement the fused backward kernel is compared with."""
+    krot, K = idx_ij.shape
+    rows = y.numel() // K
+    t, g = y.reshape(rows, K), grad_out.reshape(rows, K).contiguous()
+    base = (torch.arange(K, device=idx_ij.device) // G * G).view(K // 2, 2)[:, 0]
+    grad_theta = torch.zeros(krot, K // 2, dtype=torch.float32, device=y.device)
+    for r in reversed(range(krot)):
+        pr = idx_ij[r].view(K // 2, 2).long()
+        ci, cj = pr[:, 0] + base, pr[:, 1] + base
+        grad_theta[r] = (g[:, ci].float() * t[:, cj].float() - g[:, cj].float() * t[:, ci].float()).sum(0)
+        inv = -theta[r:r + 1]
+        t = torch.ops.rotation.rotate(t, idx_ij[r:r + 1], inv, None, G)
+        g = torch.ops.rotation.rotate(g, idx_ij[r:r + 1], inv, None, G)
+    if scale is None:
+        return g.view_as(x), grad_theta, None
+    return (g.float() * scale.float().reshape(-1)).to(x.dtype).view_as(x), grad_theta, (x.reshape(rows, K).float() * g.float()).sum(0)
+
+
+@pytest.mark.parametrize("dt,G,krot,M,with_scale", [
+    (torch.float32, 128, 8, 1037, True),       # many row blocks per warp, ragged last block
+    (torch.float32, 64, 8, 333, True),
+    (torch.float32, 128, 3, 5, False),         # no channel scales, krot != 8
+    (torch.bfloat16, 128, 8, 260, True),       # t and g rounded to bf16 after every rotation, like the per-rotation launches
+    (torch.float16, 64, 16, 77, True),
+])
+def test_fused_backward_equals_the_stagewise_walk(ops, dt, G, krot, M, with_scale):
+    from paroquant_b200 import _cabi
+    K = 1024
+    L = make_synthetic_layer(K, [64], group_size=G, krot=krot, seed=31)
+    pr, th = L.pairs[0].cuda(), L.theta[0].float().cuda()
+    sc = L.channel_scales[0].float().cuda().view(-1) if with_scale else None
+    x = torch.randn(M, K, device="cuda").to(dt)
+    go = torch.randn(M, K, device="cuda").to(dt)
+    y = torch.ops.rotation.rotate(x, pr, th, sc, G)
+    gx, gth, gsc = _cabi.rotate_backward(y, go, x, pr, th, sc, G)
+    rx, rth, rsc = _backward_stagewise(x, pr, th, y, go, sc, G)
+    # grad_x: the same arithmetic at the same rounding points -> identical
+    assert torch.equal(gx, rx)
+    # row sums: fp32 atomics in another order than torch's reduction
+    assert (gth - rth).norm() / rth.norm() < 1e-5
+    if with_scale:
+        assert (gsc - rsc).norm() / rsc.norm() < 1e-5
+    else:
+        assert gsc is None
+
+
+def test_autograd_group64_bf16_runs_through_the_op(ops):
+    from paroquant_b200.kernels.cuda import scaled_pairwise_rotation
+    K, G, M = 512, 64, 9
+    L = make_synthetic_layer(K, [64], group_size=G, seed=12)
+    pr = L.pairs[0].cuda()
+    th = L.theta[0].cuda().requires_grad_(True)                       # fp16 parameter: grad comes back in fp16
+    sc = L.channel_scales[0].cuda().requires_grad_(True)              # [1, K]
+    x = torch.randn(2, M, K, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    scaled_pairwise_rotation(x, pr, th, sc, G).float().square().sum().backward()
+    assert x.grad.shape == x.shape and x.grad.dtype == torch.bfloat16
+    assert th.grad.shape == th.shape and th.grad.dtype == th.dtype and sc.grad.shape == sc.shape
+    # an orthogonal map preserves the norm: d/dtheta of |y|^2 vanishes up to rounding, d/dx = 2 x s^2
+    ref = 2 * x.detach().float() * sc.detach().float().reshape(-1) ** 2
+    assert (x.grad.float() - ref).norm() / ref.norm() < 2e-2
+    assert th.grad.float().abs().max() < 0.05 * x.detach().float().square().sum().sqrt()
