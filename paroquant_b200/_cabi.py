@@ -7,11 +7,12 @@ call raises (the reference raises RuntimeError from TORCH_CHECK the same way).
 from __future__ import annotations
 
 import ctypes
+import os
 from pathlib import Path
 
 import torch
 
-_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libparo_b200.so"
+_LIB_PATH = Path(os.environ.get("PARO_B200_LIB") or Path(__file__).resolve().parent / "lib" / "libparo_b200.so")   # (override: A/B runs of kernel variants)
 PARO_MAX_PARTS = 8
 F32, F16, BF16 = 0, 1, 2
 _DTYPE_CODE = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}

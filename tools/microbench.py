@@ -28,11 +28,11 @@ SHAPES = {"q_o": (4096, [4096]), "kv": (4096, [1024]), "qkv": (4096, [4096, 1024
           "l2_up": (4096, [11008]), "l2_down": (11008, [4096])}
 
 
-def time_shape(name, M, reps=20, graph=True):
+def time_shape(name, M, reps=20, graph=True, group=128):
     K, parts = SHAPES[name]
     wbytes = K * sum(parts) // 2
     nsets = max(3, int(400e6 // wbytes) + 1)
-    ks = [ParoLinearKernel.from_buffers(make_synthetic_layer(K, parts, seed=900 + i, device="cuda"), torch.bfloat16,
+    ks = [ParoLinearKernel.from_buffers(make_synthetic_layer(K, parts, group_size=group, seed=900 + i, device="cuda"), torch.bfloat16,
                                         check_pairs=False, max_m=M) for i in range(nsets)]
     x = make_synthetic_activations(M, K, seed=1, device="cuda")
     y = torch.empty(M, sum(parts), dtype=torch.bfloat16, device="cuda")
@@ -76,11 +76,12 @@ if __name__ == "__main__":
     ap.add_argument("--ms", default="1,4,16")
     ap.add_argument("--shapes", default="q_o,kv,qkv,gate_up,down")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--group", type=int, default=128, help="quantisation / rotation group size (64: two scale / zero sets per record)")
     a = ap.parse_args()
     res = []
     for name in a.shapes.split(","):
         for M in [int(v) for v in a.ms.split(",")]:
-            r = time_shape(name, M, graph=not a.no_graph)
+            r = time_shape(name, M, graph=not a.no_graph, group=a.group)
             res.append(r)
             print(f"{name:12s} M={M:3d} {r['us']:8.2f} us  {r['GBps']:7.0f} GB/s  {100 * r['frac_hbm']:5.1f}% of {r['peak_source']} HBM", flush=True)
             torch.cuda.empty_cache()
