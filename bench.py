@@ -416,6 +416,11 @@ def run_ours(args):
         if world == 1 and not args.no_prefill:
             line["prefill"] = prefill_section(dev)
             line["decode_batches"] = decode_batches_section(dev)
+        if world == 1 and not args.no_prefill:
+            try:
+                line["training_op"] = training_op_section()
+            except Exception as e:   # a side measurement must never cost the bench line
+                line["training_op"] = {"unavailable": repr(e)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample(M)
         print(json.dumps(line), flush=True)
@@ -458,6 +463,30 @@ def reference_gpu_section(M, ours_tok_s, per_linear):
     if per_linear is not None:
         sec["ratio_per_linear_api"] = per_linear["tokens_per_s"] / tok_s
     return sec
+
+
+def training_op_section():
+    """the rotate op's backward on fp32 [4096, 4096] (the optimiser's dtype), ONE launch (paro_rotate_backward)
+    against the reference's backward structure -- a Python walk over the 8 rotations with per-rotation launches, gathers and
+    reductions (kernels/cuda/autograd.py:20-61) -- run on our own rotate kernel on the same box (tools/backward_bench.py)."""
+    import torch
+
+    import paroquant_b200.kernels.cuda  # noqa: F401
+    from paroquant_b200 import _cabi
+    from paroquant_b200.checkpoint import make_synthetic_layer
+    from tools.backward_bench import stagewise, timed
+
+    M, K, G = 4096, 4096, 128
+    L = make_synthetic_layer(K, [64], seed=5, device="cuda")
+    pr, th, sc = L.pairs[0], L.theta[0].float(), L.channel_scales[0].float().view(-1)
+    x = torch.randn(M, K, device="cuda")
+    go = torch.randn(M, K, device="cuda")
+    y = torch.ops.rotation.rotate(x, pr, th, sc, G)
+    fwd = timed(lambda: torch.ops.rotation.rotate(x, pr, th, sc, G))
+    fused = timed(lambda: _cabi.rotate_backward(y, go, x, pr, th, sc, G))
+    walk = timed(lambda: stagewise(x, pr, th, y, go, sc, G), reps=5)
+    return {"shape": [M, K], "dtype": "f32", "krot": 8, "forward_us": fwd, "fused_backward_us": fused, "stagewise_walk_us": walk,
+            "speedup_vs_walk": walk / fused, "fused_backward_GBps": 4 * M * K * 4 / fused / 1e3}
 
 
 def prefill_section(dev):

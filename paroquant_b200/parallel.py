@@ -22,8 +22,8 @@ from .checkpoint import ParoLayerBuffers
 def shard_rows(b: ParoLayerBuffers, rank: int, world: int) -> ParoLayerBuffers:
     """Row-parallel shard: input channels [rank*K/world, (rank+1)*K/world)."""
     K, G = b.in_features, b.group_size
-    if K % (world * G):
-        raise ValueError(f"in_features={K} cannot be split {world}-way on {G}-channel group boundaries")
+    if K % (world * max(G, 128)):   # a weight record always covers 128 channels (two groups when group_size is 64)
+        raise ValueError(f"in_features={K} cannot be split {world}-way on {max(G, 128)}-channel group boundaries")
     ks = K // world
     k0 = rank * ks
     return ParoLayerBuffers(

@@ -74,6 +74,24 @@ def test_round_trip_detection_and_merge(tmp_path):
     assert "model.layers.0.self_attn.o_proj" not in ck2.layers and "model.layers.0.self_attn.o_proj.qweight" in ck2.dense
 
 
+def test_round_trip_group64(tmp_path):
+    """A group_size = 64 checkpoint (convert.py rotates and quantises in groups of `group_size`) loads into group-64 buffers
+    that the fused kernels accept (shape check through the C-ABI, no GPU)."""
+    from paroquant_b200 import _cabi
+    L = make_synthetic_layer(256, [128], group_size=64, seed=21)
+    cio.save_paro_checkpoint(tmp_path, _names("model.layers.0.mlp.down_proj", L), bits=4, group_size=64, krot=8)
+    ck = cio.load_paro_checkpoint(tmp_path)
+    got = ck.layers["model.layers.0.mlp.down_proj"]
+    assert got.group_size == 64 and got.qzeros.shape == (4, 16) and got.scales.shape == (4, 128)
+    for name in ("qweight", "qzeros", "scales", "theta", "pairs", "channel_scales"):
+        assert torch.equal(getattr(got, name), getattr(L, name)), name
+    shape = _cabi.make_shape(got.in_features, got.part_sizes, got.group_size, got.krot, torch.float16)
+    assert _cabi.packed_bytes(shape) > 2 * 8960                      # 1 block x 2 record groups, two scale / zero sets each
+    (tmp_path / "config.json").write_text(json.dumps({"quantization_config": {"quant_method": "paroquant", "bits": 4, "group_size": 32, "krot": 8}}))
+    with pytest.raises(ValueError, match="group_size 64 or 128"):
+        cio.load_paro_checkpoint(tmp_path)
+
+
 def test_loader_errors(tmp_path):
     _write_model(tmp_path)
     (tmp_path / "config.json").write_text(json.dumps({"quantization_config": {"quant_method": "awq"}}))

@@ -67,6 +67,28 @@ def test_row_shards_recompose(oracle):
         shard_rows(make_synthetic_layer(1280, [64]), 0, 4)   # 10 groups, like 11008/8 = 10.75
 
 
+def test_row_shards_recompose_group64(oracle):
+    """group_size 64: rotation and quantisation groups are 64 channels, a shard still has to be a whole number of 128-channel
+    weight records; the oracle on the shards adds up to the oracle on the full layer."""
+    full = make_synthetic_layer(512, [64], group_size=64, seed=19)
+    x = torch.randn(2, 512).numpy()
+    d = full.numpy_dict()
+    assert d["group"] == 64 and d["qzeros"].shape[0] == 8
+    xr = oracle.c_rotate(x, d["pairs"][0], d["theta"][0], d["channel_scales"][0], 64, "float16")
+    acc_full = xr.astype(np.float64) @ oracle.c_dequant(d["qweight"], d["qzeros"], d["scales"], 64, "float16").astype(np.float64)
+    acc = 0
+    for r in range(2):
+        s = shard_rows(full, r, 2)
+        assert s.in_features == 256 and s.group_size == 64 and s.qzeros.shape[0] == 4
+        ds = s.numpy_dict()
+        xrs = oracle.c_rotate(x[:, r * 256:(r + 1) * 256], ds["pairs"][0], ds["theta"][0], ds["channel_scales"][0], 64, "float16")
+        assert (xrs == xr[:, r * 256:(r + 1) * 256]).all()
+        acc = acc + xrs.astype(np.float64) @ oracle.c_dequant(ds["qweight"], ds["qzeros"], ds["scales"], 64, "float16").astype(np.float64)
+    assert np.allclose(acc, acc_full, rtol=1e-12, atol=1e-12)
+    with pytest.raises(ValueError, match="128-channel group boundaries"):
+        shard_rows(make_synthetic_layer(384, [64], group_size=64), 0, 2)   # 192 channels per rank: whole groups, but half a record
+
+
 def test_column_shards_recompose(oracle):
     full = make_synthetic_layer(256, [64, 32], seed=10, bias=True)
     d = full.numpy_dict()
