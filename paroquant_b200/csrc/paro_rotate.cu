@@ -393,7 +393,9 @@ int rotate_launch(const void *x, void *out, const int16_t *idx, const void *thet
 //     (t, g) <- Givens(-theta) (t, g)                    (orthogonal: the same update back-propagates g), rounded to T per
 //                                                         rotation exactly where the per-rotation launches rounded
 // and after the last un-rotation grad_x = g * scale, dL/dscale += x * g.  dL/dtheta and dL/dscale are accumulated per warp over
-// its row blocks in registers and added to fp32 buffers with one atomic per (rotation, pair) / channel and warp.
+// its row blocks and added to fp32 buffers with one atomic per (rotation, pair) / channel and warp.  A warp keeps ONE group for
+// all its row blocks, so the group's pair slots and (cos, sin) are computed once into shared memory: the first version re-read
+// indices and angles from L2 in every rotation of every row block and sat on those loads (13 long-scoreboard stalls per issue).
 template <typename T, int G>
 __global__ void __launch_bounds__(128) rotate_backward_kernel(const T *__restrict__ y, const T *__restrict__ gout, const T *__restrict__ x,
                                                               const int16_t *__restrict__ idx, const void *__restrict__ theta, int theta_dtype,
@@ -409,13 +411,28 @@ __global__ void __launch_bounds__(128) rotate_backward_kernel(const T *__restric
   const int g = static_cast<int>(wid % groups), split = static_cast<int>(wid / groups);
   const int64_t row_blocks = (M + RB - 1) / RB;
   float4 *tt = tile_t[warp], *tg = tile_g[warp];
-  // dL/dtheta partials of this warp: [rotation][pair], each lane touches only its own pairs (shared memory, not registers: the
-  // rotation loop stays rolled -- unrolled over 16 rotations the kernel needed 160-190 registers)
-  __shared__ float acc_th[4][16][G / 2];
-  float (*acc)[G / 2] = acc_th[warp];
-  for (int r = 0; r < krot; ++r)
+  // per warp, dynamic shared memory: [rotation][q][lane] {cos, sin} (float2), pair slots (i | j << 16), dL/dtheta partial -- each
+  // lane touches only the entries of its own pairs (shared memory, not registers: the rotation loop stays rolled; unrolled over
+  // 16 rotations the kernel needed 160-190 registers)
+  extern __shared__ __align__(16) uint8_t bw_dyn[];
+  constexpr int kPerRot = G / 2;   // pairs per rotation = PPL * 32
+  float2 *mcs = reinterpret_cast<float2 *>(bw_dyn) + static_cast<size_t>(warp) * krot * kPerRot;
+  uint32_t *mij = reinterpret_cast<uint32_t *>(bw_dyn + static_cast<size_t>(4) * krot * kPerRot * 8) + static_cast<size_t>(warp) * krot * kPerRot;
+  float *acc = reinterpret_cast<float *>(bw_dyn + static_cast<size_t>(4) * krot * kPerRot * 12) + static_cast<size_t>(warp) * krot * kPerRot;
+  for (int r = 0; r < krot; ++r) {
 #pragma unroll
-    for (int q = 0; q < PPL; ++q) acc[r][lane * PPL + q] = 0.f;
+    for (int q = 0; q < PPL; ++q) {
+      const int t = lane * PPL + q, e = r * kPerRot + q * 32 + lane;
+      const int ij = *reinterpret_cast<const int *>(idx + static_cast<int64_t>(r) * K + g * G + 2 * t);
+      const float th = load_param_as<T>(theta, static_cast<int64_t>(r) * (K / 2) + g * (G / 2) + t, theta_dtype);
+      float sn, cs;
+      __sincosf(-th, &sn, &cs);
+      mcs[e] = make_float2(cs, sn);
+      mij[e] = static_cast<uint32_t>(rot_slot(ij & 0xFFFF)) | (static_cast<uint32_t>(rot_slot((ij >> 16) & 0xFFFF)) << 16);
+      acc[e] = 0.f;
+    }
+  }
+  __syncwarp();
   float acc_s[CPL], sc[CPL];
 #pragma unroll
   for (int c = 0; c < CPL; ++c) {
@@ -445,14 +462,13 @@ __global__ void __launch_bounds__(128) rotate_backward_kernel(const T *__restric
       {
 #pragma unroll
         for (int q = 0; q < PPL; ++q) {
-          const int t = lane * PPL + q;
-          const int ij = *reinterpret_cast<const int *>(idx + static_cast<int64_t>(r) * K + g * G + 2 * t);
-          const int pi = rot_slot(ij & 0xFFFF), pj = rot_slot((ij >> 16) & 0xFFFF);
-          const float th = load_param_as<T>(theta, static_cast<int64_t>(r) * (K / 2) + g * (G / 2) + t, theta_dtype);
-          float sn, cs;
-          __sincosf(-th, &sn, &cs);
+          const int e = r * kPerRot + q * 32 + lane;
+          const uint32_t ijw = mij[e];
+          const int pi = ijw & 0xFFFF, pj = ijw >> 16;
+          const float2 csn = mcs[e];
+          const float cs = csn.x, sn = csn.y;
           float4 ti = tt[pi], tj = tt[pj], gi = tg[pi], gj = tg[pj];
-          acc[r][t] += (gi.x * tj.x - gj.x * ti.x) + (gi.y * tj.y - gj.y * ti.y) + (gi.z * tj.z - gj.z * ti.z) + (gi.w * tj.w - gj.w * ti.w);
+          acc[e] += (gi.x * tj.x - gj.x * ti.x) + (gi.y * tj.y - gj.y * ti.y) + (gi.z * tj.z - gj.z * ti.z) + (gi.w * tj.w - gj.w * ti.w);
           float4 ni, nj, mi, mj;
           givens(cs, sn, ti.x, tj.x, ni.x, nj.x); givens(cs, sn, ti.y, tj.y, ni.y, nj.y);
           givens(cs, sn, ti.z, tj.z, ni.z, nj.z); givens(cs, sn, ti.w, tj.w, ni.w, nj.w);
@@ -485,7 +501,7 @@ __global__ void __launch_bounds__(128) rotate_backward_kernel(const T *__restric
   }
   for (int r = 0; r < krot; ++r) {
 #pragma unroll
-    for (int q = 0; q < PPL; ++q) atomicAdd(grad_theta + static_cast<int64_t>(r) * (K / 2) + g * (G / 2) + lane * PPL + q, acc[r][lane * PPL + q]);
+    for (int q = 0; q < PPL; ++q) atomicAdd(grad_theta + static_cast<int64_t>(r) * (K / 2) + g * (G / 2) + lane * PPL + q, acc[r * kPerRot + q * 32 + lane]);
   }
   if (grad_scale) {
 #pragma unroll
@@ -498,21 +514,28 @@ static int launch_backward_T(const void *y, const void *gout, const void *x, con
                              int scales_dtype, void *grad_x, float *grad_theta, float *grad_scale, int64_t M, int K, int krot, int G, cudaStream_t stream) {
   const int groups = K / G;
   const int64_t row_blocks = (M + 3) / 4;
-  // enough warps to fill the machine (148 SMs x 6 resident CTAs of 4 warps: 80 registers, 32 KB), no more splits than row blocks:
-  // every warp then walks ~row_blocks / splits blocks of its group and pays its atomics once
-  int64_t splits = (148 * 6 * 4 + groups - 1) / groups;
+  // per CTA: 4 warps x krot x G/2 pairs x ({cos, sin} 8 B + slots 4 B + partial 4 B) of dynamic shared memory + the two tiles
+  const size_t dyn = static_cast<size_t>(4) * krot * (G / 2) * 16;
+  const int resident = static_cast<int>((227 * 1024) / (dyn + static_cast<size_t>(8) * G * 16 + 1024));
+  const int ctas_per_sm = resident < 1 ? 1 : resident > 6 ? 6 : resident;   // 6: the register limit
+  // enough warps to fill the machine, no more splits than row blocks: every warp then walks ~row_blocks / splits blocks of its
+  // group, computes the group's (cos, sin) once and pays its atomics once
+  int64_t splits = (148 * ctas_per_sm * 4 + groups - 1) / groups;
   if (splits > row_blocks) splits = row_blocks;
   if (splits < 1) splits = 1;
   const int64_t blocks = (splits * groups + 3) / 4;
   if (blocks > 0x7FFFFFFF) { set_error("rotate_backward: too many groups"); return PARO_EINVAL; }
   const T *yp = static_cast<const T *>(y), *gp = static_cast<const T *>(gout), *xp = static_cast<const T *>(x);
   T *gx = static_cast<T *>(grad_x);
-  if (G == 128)
-    rotate_backward_kernel<T, 128><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(yp, gp, xp, idx, theta, theta_dtype, scales, scales_dtype, gx, grad_theta,
-                                                                                     grad_scale, M, K, krot, static_cast<int>(splits));
-  else
-    rotate_backward_kernel<T, 64><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(yp, gp, xp, idx, theta, theta_dtype, scales, scales_dtype, gx, grad_theta,
-                                                                                    grad_scale, M, K, krot, static_cast<int>(splits));
+  if (G == 128) {
+    PARO_CUDA_OK(cudaFuncSetAttribute(rotate_backward_kernel<T, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
+    rotate_backward_kernel<T, 128><<<static_cast<unsigned>(blocks), 128, dyn, stream>>>(yp, gp, xp, idx, theta, theta_dtype, scales, scales_dtype, gx, grad_theta,
+                                                                                       grad_scale, M, K, krot, static_cast<int>(splits));
+  } else {
+    PARO_CUDA_OK(cudaFuncSetAttribute(rotate_backward_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
+    rotate_backward_kernel<T, 64><<<static_cast<unsigned>(blocks), 128, dyn, stream>>>(yp, gp, xp, idx, theta, theta_dtype, scales, scales_dtype, gx, grad_theta,
+                                                                                      grad_scale, M, K, krot, static_cast<int>(splits));
+  }
   PARO_CUDA_OK(cudaGetLastError());
   note_launches(1);
   return PARO_OK;
