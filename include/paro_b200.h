@@ -90,7 +90,10 @@ int paro_rotate(const void *x, void *out, const int16_t *idx_ij, const void *the
  *   grad_theta  device [krot, K/2] fp32, ACCUMULATED into (zero it first)
  *   grad_scale  device [K] fp32, accumulated into, or NULL (then scales may be NULL too)
  * t and g are rounded to `dtype` after every rotation, where the reference's per-rotation
- * launches store them; the sums over rows run in fp32 (atomics: order-dependent last bits). */
+ * launches store them; the sums over rows run in fp32 (atomics: order-dependent last bits).
+ * grad_theta is the gradient, sum_rows (g_i t_j - g_j t_i) per pair; the reference's expression
+ * (autograd.py:50-52, applied after g was un-rotated too) evaluates to cos * that - sin * sum_rows(g . t)
+ * -- see paroquant_b200/kernels/cuda/autograd.py.  grad_x and grad_scale equal the reference's.        */
 int paro_rotate_backward(const void *y, const void *grad_out, const void *x, const int16_t *idx_ij,
                          const void *theta, int32_t theta_dtype, const void *scales, int32_t scales_dtype,
                          void *grad_x, float *grad_theta, float *grad_scale, int64_t M, int32_t K,

@@ -248,6 +248,46 @@ def np_rotate(x_f32, pairs, theta_f32, scales_f32=None, group: int = 128, dtype:
     return v.reshape(x.shape)
 
 
+def np_rotate_backward(x_f32, pairs, theta_f32, y_f32, grad_out_f32, scales_f32=None, group: int = 128, reference_formula: bool = False):
+    """RotateTensorFunc.backward in float64, structured like kernels/cuda/autograd.py:20-61: walk the rotations last to first,
+    un-rotate t and g with -theta, form dtheta from the un-rotated values; grad_x = g * scale, grad_scale = sum_rows(x * g)
+    (autograd.py:54-56).  No per-rotation rounding: the mathematical gradient the per-dtype kernels are compared with.
+
+    dtheta: with (a, b) / (ga, gb) the un-rotated values / gradients of a pair, the gradient is the 2-D cross product
+        dL/dtheta = sum_rows (ga*b - gb*a)                       (rotation invariant: equals sum_rows (G_i y_j - G_j y_i))
+    which is what this function and the CUDA backward return (checked against autograd of a dense formulation, tests/test_oracle.py).
+    The reference evaluates  (ga*b - gb*a) * cos - (ga*a + gb*b) * sin  (autograd.py:50-52) -- the right expression for the
+    OUTPUT-space gradient G and the INPUT values (a, b), but it is applied after g has been un-rotated too (autograd.py:38), so it
+    returns  cos * dL/dtheta - sin * sum_rows(g . t):  `reference_formula=True` reproduces that value for comparison.
+    Returns (grad_x, grad_theta [krot, K/2], grad_scale [K] or None)."""
+    idx = np.ascontiguousarray(pairs, dtype=np.int16)
+    krot, K = idx.shape
+    ng = K // group
+    x = np.asarray(x_f32, np.float64).reshape(-1, K)
+    t = np.asarray(y_f32, np.float64).reshape(-1, K).reshape(-1, ng, group).copy()
+    g = np.asarray(grad_out_f32, np.float64).reshape(-1, K).reshape(-1, ng, group).copy()
+    th = np.asarray(theta_f32, np.float64)
+    grad_theta = np.zeros((krot, K // 2), np.float64)
+    off = np.arange(ng)[:, None]
+    for r in range(krot - 1, -1, -1):
+        p = idx[r].astype(np.int64).reshape(ng, group)
+        pi, pj = p[:, 0::2], p[:, 1::2]
+        ang = th[r].reshape(ng, group // 2)
+        c_, s_ = np.cos(ang)[None], np.sin(ang)[None]
+        for v in (t, g):                                           # rotate(., idx, -theta): [[c, -s], [s, c]]
+            a, b = v[:, off, pi].copy(), v[:, off, pj].copy()
+            v[:, off, pi] = c_ * a - s_ * b
+            v[:, off, pj] = s_ * a + c_ * b
+        a, b, ga, gb = t[:, off, pi], t[:, off, pj], g[:, off, pi], g[:, off, pj]
+        cross = (ga * b - gb * a).sum(0)
+        grad_theta[r] = ((cross * c_[0] - (ga * a + gb * b).sum(0) * s_[0]) if reference_formula else cross).reshape(-1)
+    gflat = g.reshape(-1, K)
+    if scales_f32 is None:
+        return gflat.reshape(np.shape(x_f32)), grad_theta, None
+    sc = np.asarray(scales_f32, np.float64).reshape(-1)
+    return (gflat * sc[None, :]).reshape(np.shape(x_f32)), grad_theta, (x * gflat).sum(0)
+
+
 # ------------------------------------------------------------------ GEMM / linear
 
 def np_gemm(xrot_f32, W_f32, bias_f32=None, dtype: str = "bfloat16", return_acc: bool = False):

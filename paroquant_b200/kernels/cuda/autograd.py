@@ -12,6 +12,13 @@ launches, five gathers and a reduction).  It uses the identities
 on the stage OUTPUT (t) and its gradient (g), then un-rotates both with -theta (a Givens
 rotation is orthogonal, so the same update back-propagates g), rounding t and g to x.dtype after
 every rotation exactly where the per-rotation launches stored them; the row sums run in fp32.
+
+Deviation from the reference, on purpose: grad_theta here is the gradient (checked against autograd through a dense
+formulation, tests/test_gpu_rotate.py, tests/test_oracle.py).  The reference evaluates
+`(ga*b - gb*a)*cos - (ga*a + gb*b)*sin` (autograd.py:50-52) -- the right expression for the OUTPUT-space gradient and the
+INPUT values of a pair -- after it has un-rotated g as well (autograd.py:38), which makes it return
+`cos * dL/dtheta - sin * sum_rows(g . t)`; `oracle.np_rotate_backward(..., reference_formula=True)` reproduces that value.
+grad_x and grad_scale are the reference's.
 """
 from __future__ import annotations
 

@@ -99,6 +99,57 @@ def test_rotate_group64_and_krot1(oracle):
     assert abs(float(a[0, i]) - float(exp_i)) <= 2e-3 * max(1.0, abs(float(exp_i)))
 
 
+@pytest.mark.parametrize("G,krot,with_scale", [(128, 8, True), (64, 3, True), (128, 2, False)])
+def test_rotate_backward_matches_autograd_of_the_dense_formulation(oracle, G, krot, with_scale):
+    """oracle.np_rotate_backward (the reference's backward formulas, autograd.py:20-61, in float64) against torch autograd
+    through an explicit dense float64 formulation of the same rotation: gradients w.r.t. x, theta and the channel scales."""
+    K, M = 256, 5
+    L = make_synthetic_layer(K, [64], group_size=G, krot=krot, seed=23)
+    pr = L.pairs[0]
+    th = L.theta[0].double().requires_grad_(True)
+    sc = L.channel_scales[0].double().view(-1).requires_grad_(with_scale)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(M, K, generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(M, K, generator=g, dtype=torch.float64)
+
+    def dense(x, th, sc):
+        v = x * sc if with_scale else x
+        base = (torch.arange(K) // G * G).view(K // 2, 2)[:, 0]
+        for r in range(krot):
+            p = pr[r].view(K // 2, 2).long()
+            i, j = p[:, 0] + base, p[:, 1] + base
+            c, s = th[r].cos(), th[r].sin()
+            vi, vj = v[:, i], v[:, j]
+            v = v.clone()
+            v[:, i] = c * vi + s * vj                            # Appendix A.2: [[c, s], [-s, c]]
+            v[:, j] = c * vj - s * vi
+        return v
+
+    y = dense(x, th, sc)
+    (y * w).sum().backward()
+    gx, gth, gsc = oracle.np_rotate_backward(x.detach().numpy(), pr.numpy(), th.detach().numpy(), y.detach().numpy(), w.numpy(),
+                                             sc.detach().numpy() if with_scale else None, G)
+    assert np.allclose(gx, x.grad.numpy(), rtol=1e-10, atol=1e-12)
+    assert np.allclose(gth, th.grad.numpy(), rtol=1e-9, atol=1e-11)
+    if with_scale:
+        assert np.allclose(gsc, sc.grad.numpy(), rtol=1e-10, atol=1e-12)
+    else:
+        assert gsc is None
+    # the expression the reference evaluates (autograd.py:50-52, after un-rotating g as well) is NOT this gradient: it returns
+    # cos * dL/dtheta - sin * sum_rows(g . t); same grad_x / grad_scale
+    gx2, gth_ref, _ = oracle.np_rotate_backward(x.detach().numpy(), pr.numpy(), th.detach().numpy(), y.detach().numpy(), w.numpy(),
+                                                sc.detach().numpy() if with_scale else None, G, reference_formula=True)
+    assert np.array_equal(gx2, gx)
+    assert not np.allclose(gth_ref, th.grad.numpy(), rtol=1e-3, atol=1e-6)
+    last = th.detach().numpy()[krot - 1]
+    base = (np.arange(K) // G * G).reshape(K // 2, 2)[:, 0]
+    pl = pr[krot - 1].numpy().astype(np.int64).reshape(K // 2, 2)
+    i, j = pl[:, 0] + base, pl[:, 1] + base
+    yn, wn = y.detach().numpy(), w.numpy()
+    dot = (wn[:, i] * yn[:, i] + wn[:, j] * yn[:, j]).sum(0)      # g . t of a pair is rotation invariant: use the stage output
+    assert np.allclose(gth_ref[krot - 1], np.cos(last) * th.grad.numpy()[krot - 1] - np.sin(last) * dot, rtol=1e-9, atol=1e-11)
+
+
 def test_linear_equals_pseudo_weight_identity(oracle):
     """Appendix A.4: rotate(x * cs) . W == x . (cs * R^T W) -- checked in fp32 on a tiny layer."""
     _, d = _layer(K=256, parts=(32,), seed=11)
