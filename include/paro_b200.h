@@ -91,13 +91,18 @@ int paro_rotate(const void *x, void *out, const int16_t *idx_ij, const void *the
  *   grad_scale  device [K] fp32, accumulated into, or NULL (then scales may be NULL too)
  * t and g are rounded to `dtype` after every rotation, where the reference's per-rotation
  * launches store them; the sums over rows run in fp32 (atomics: order-dependent last bits).
- * grad_theta is the gradient, sum_rows (g_i t_j - g_j t_i) per pair; the reference's expression
- * (autograd.py:50-52, applied after g was un-rotated too) evaluates to cos * that - sin * sum_rows(g . t)
- * -- see paroquant_b200/kernels/cuda/autograd.py.  grad_x and grad_scale equal the reference's.        */
+ * theta_formula  PARO_THETA_GRADIENT: grad_theta = sum_rows (g_i t_j - g_j t_i) per pair, the gradient;
+ *                PARO_THETA_REFERENCE_EXPRESSION: the value the reference's expression takes
+ *                (autograd.py:50-52, applied after g was un-rotated too, autograd.py:38):
+ *                cos * gradient - sin * sum_rows(g . t) -- see paroquant_b200/kernels/cuda/autograd.py.
+ * grad_x and grad_scale equal the reference's either way.                                            */
+#define PARO_THETA_GRADIENT 0
+#define PARO_THETA_REFERENCE_EXPRESSION 1
 int paro_rotate_backward(const void *y, const void *grad_out, const void *x, const int16_t *idx_ij,
                          const void *theta, int32_t theta_dtype, const void *scales, int32_t scales_dtype,
                          void *grad_x, float *grad_theta, float *grad_scale, int64_t M, int32_t K,
-                         int32_t krot, int32_t group_size, int32_t dtype, paro_stream_t stream);
+                         int32_t krot, int32_t group_size, int32_t dtype, int32_t theta_formula,
+                         paro_stream_t stream);
 
 /* Size in bytes of the kernel-layout buffer paro_prepack fills (0 on invalid shape). */
 size_t paro_packed_bytes(const paro_linear_shape *shape);

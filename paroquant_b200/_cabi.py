@@ -75,7 +75,7 @@ def lib() -> ctypes.CDLL:
         L.paro_rotate.restype = ctypes.c_int
         L.paro_rotate.argtypes = [vp, vp, vp, vp, i32, vp, i32, i64, i32, i32, i32, i32, vp]
         L.paro_rotate_backward.restype = ctypes.c_int
-        L.paro_rotate_backward.argtypes = [vp, vp, vp, vp, vp, i32, vp, i32, vp, vp, vp, i64, i32, i32, i32, i32, vp]
+        L.paro_rotate_backward.argtypes = [vp, vp, vp, vp, vp, i32, vp, i32, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp]
         L.paro_packed_bytes.restype = sz
         L.paro_packed_bytes.argtypes = [shp]
         L.paro_prepack.restype = ctypes.c_int
@@ -181,9 +181,10 @@ def rotate(x: torch.Tensor, idx_ij: torch.Tensor, theta: torch.Tensor, scales: t
 
 
 def rotate_backward(y: torch.Tensor, grad_out: torch.Tensor, x: torch.Tensor, idx_ij: torch.Tensor, theta: torch.Tensor,
-                    scales: torch.Tensor | None = None, group_size: int = 128):
+                    scales: torch.Tensor | None = None, group_size: int = 128, reference_formula: bool = False):
     """Backward of `rotate` in one launch: (grad_x, grad_theta fp32 [krot, K/2], grad_scale fp32 [K] | None).
-    Replaces the per-rotation Python walk of kernels/cuda/autograd.py:20-61."""
+    Replaces the per-rotation Python walk of kernels/cuda/autograd.py:20-61.  reference_formula: grad_theta takes the value of the
+    reference's expression (cos * gradient - sin * sum_rows(g . t)) instead of the gradient."""
     dev = _need_cuda(y, grad_out, x, idx_ij, theta, scales)
     if idx_ij.dtype != torch.int16:
         raise RuntimeError("idx_ij must be int16")
@@ -207,7 +208,7 @@ def rotate_backward(y: torch.Tensor, grad_out: torch.Tensor, x: torch.Tensor, id
                                         dtype_code(theta.dtype), scales.data_ptr() if has_scale else None,
                                         dtype_code(scales.dtype) if has_scale else 0, grad_x.data_ptr(), grad_theta.data_ptr(),
                                         grad_scale.data_ptr() if has_scale else None, M, K, idx_ij.size(0), group_size,
-                                        dtype_code(y.dtype), _stream(dev))
+                                        dtype_code(y.dtype), 1 if reference_formula else 0, _stream(dev))
     _check(rc, "rotate_backward")
     return grad_x, grad_theta, grad_scale
 

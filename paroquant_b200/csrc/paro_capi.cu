@@ -27,7 +27,7 @@ int rotate_launch(const void *x, void *out, const int16_t *idx, const void *thet
                   int scales_dtype, int64_t M, int K, int krot, int G, int dtype, cudaStream_t stream);
 int rotate_backward_launch(const void *y, const void *gout, const void *x, const int16_t *idx, const void *theta, int theta_dtype, const void *scales,
                            int scales_dtype, void *grad_x, float *grad_theta, float *grad_scale, int64_t M, int K, int krot, int G, int dtype,
-                           cudaStream_t stream);
+                           int ref_formula, cudaStream_t stream);
 int prepack_launch(const paro_linear_shape &s, const Layout &L, const int32_t *qweight, const int32_t *qzeros,
                    const void *scales, int scales_dtype, const int16_t *pairs, const void *theta, int theta_dtype,
                    const void *cscales, int cs_dtype, void *packed, cudaStream_t stream);
@@ -95,8 +95,9 @@ int paro_rotate(const void *x, void *out, const int16_t *idx_ij, const void *the
 
 int paro_rotate_backward(const void *y, const void *grad_out, const void *x, const int16_t *idx_ij, const void *theta, int32_t theta_dtype,
                          const void *scales, int32_t scales_dtype, void *grad_x, float *grad_theta, float *grad_scale, int64_t M, int32_t K,
-                         int32_t krot, int32_t group_size, int32_t dtype, paro_stream_t stream) {
+                         int32_t krot, int32_t group_size, int32_t dtype, int32_t theta_formula, paro_stream_t stream) {
   g_launches = 0;
+  if (theta_formula != PARO_THETA_GRADIENT && theta_formula != PARO_THETA_REFERENCE_EXPRESSION) { set_error("rotate_backward: unknown theta_formula %d", theta_formula); return PARO_EINVAL; }
   if (!y || !grad_out || !idx_ij || !theta || !grad_x || !grad_theta) { set_error("rotate_backward: null pointer argument"); return PARO_EINVAL; }
   if (grad_scale && (!x || !scales)) { set_error("rotate_backward: grad_scale needs x and scales"); return PARO_EINVAL; }
   if (!valid_dtype(dtype)) { set_error("rotate supports Float, Half, and BFloat16, got dtype code %d", dtype); return PARO_EINVAL; }
@@ -108,7 +109,7 @@ int paro_rotate_backward(const void *y, const void *grad_out, const void *x, con
   if (grad_x == y || grad_x == grad_out) { set_error("rotate_backward: grad_x must not alias y / grad_out"); return PARO_EINVAL; }
   if (!aligned(idx_ij, 4)) { set_error("rotate_backward: idx_ij must be 4-byte aligned"); return PARO_EINVAL; }
   return rotate_backward_launch(y, grad_out, x, idx_ij, theta, theta_dtype, scales, scales_dtype, grad_x, grad_theta, grad_scale, M, K, krot, group_size,
-                                dtype, static_cast<cudaStream_t>(stream));
+                                dtype, theta_formula, static_cast<cudaStream_t>(stream));
 }
 
 size_t paro_packed_bytes(const paro_linear_shape *shape) {

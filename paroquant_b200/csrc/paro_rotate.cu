@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(128) rotate_backward_kernel(const T *__restric
                                                               const int16_t *__restrict__ idx, const void *__restrict__ theta, int theta_dtype,
                                                               const void *__restrict__ scales, int scales_dtype, T *__restrict__ grad_x,
                                                               float *__restrict__ grad_theta, float *__restrict__ grad_scale, int64_t M, int K,
-                                                              int krot, int splits) {
+                                                              int krot, int splits, int ref_formula) {
   constexpr int RB = 4, CPL = G / 32, PPL = G / 64;
   __shared__ __align__(16) float4 tile_t[4][G], tile_g[4][G];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -419,6 +419,9 @@ __global__ void __launch_bounds__(128) rotate_backward_kernel(const T *__restric
   float2 *mcs = reinterpret_cast<float2 *>(bw_dyn) + static_cast<size_t>(warp) * krot * kPerRot;
   uint32_t *mij = reinterpret_cast<uint32_t *>(bw_dyn + static_cast<size_t>(4) * krot * kPerRot * 8) + static_cast<size_t>(warp) * krot * kPerRot;
   float *acc = reinterpret_cast<float *>(bw_dyn + static_cast<size_t>(4) * krot * kPerRot * 12) + static_cast<size_t>(warp) * krot * kPerRot;
+  // ref_formula: also sum_rows (g . t) per pair, for the value the reference's expression takes (autograd.py:50-52 applied after
+  // g was un-rotated: cos * dL/dtheta - sin * sum(g . t)); the array exists only then
+  float *acc2 = reinterpret_cast<float *>(bw_dyn + static_cast<size_t>(4) * krot * kPerRot * 16) + static_cast<size_t>(warp) * krot * kPerRot;
   for (int r = 0; r < krot; ++r) {
 #pragma unroll
     for (int q = 0; q < PPL; ++q) {
@@ -430,6 +433,7 @@ __global__ void __launch_bounds__(128) rotate_backward_kernel(const T *__restric
       mcs[e] = make_float2(cs, sn);
       mij[e] = static_cast<uint32_t>(rot_slot(ij & 0xFFFF)) | (static_cast<uint32_t>(rot_slot((ij >> 16) & 0xFFFF)) << 16);
       acc[e] = 0.f;
+      if (ref_formula) acc2[e] = 0.f;
     }
   }
   __syncwarp();
@@ -469,6 +473,8 @@ __global__ void __launch_bounds__(128) rotate_backward_kernel(const T *__restric
           const float cs = csn.x, sn = csn.y;
           float4 ti = tt[pi], tj = tt[pj], gi = tg[pi], gj = tg[pj];
           acc[e] += (gi.x * tj.x - gj.x * ti.x) + (gi.y * tj.y - gj.y * ti.y) + (gi.z * tj.z - gj.z * ti.z) + (gi.w * tj.w - gj.w * ti.w);
+          if (ref_formula)   // g . t of the pair (rotation invariant, like the cross product above)
+            acc2[e] += (gi.x * ti.x + gj.x * tj.x) + (gi.y * ti.y + gj.y * tj.y) + (gi.z * ti.z + gj.z * tj.z) + (gi.w * ti.w + gj.w * tj.w);
           float4 ni, nj, mi, mj;
           givens(cs, sn, ti.x, tj.x, ni.x, nj.x); givens(cs, sn, ti.y, tj.y, ni.y, nj.y);
           givens(cs, sn, ti.z, tj.z, ni.z, nj.z); givens(cs, sn, ti.w, tj.w, ni.w, nj.w);
@@ -501,7 +507,12 @@ __global__ void __launch_bounds__(128) rotate_backward_kernel(const T *__restric
   }
   for (int r = 0; r < krot; ++r) {
 #pragma unroll
-    for (int q = 0; q < PPL; ++q) atomicAdd(grad_theta + static_cast<int64_t>(r) * (K / 2) + g * (G / 2) + lane * PPL + q, acc[r * kPerRot + q * 32 + lane]);
+    for (int q = 0; q < PPL; ++q) {
+      const int e = r * kPerRot + q * 32 + lane;
+      float v = acc[e];
+      if (ref_formula) v = mcs[e].x * v + mcs[e].y * acc2[e];   // {cos, sin}(-theta): cos(theta) * cross - sin(theta) * dot
+      atomicAdd(grad_theta + static_cast<int64_t>(r) * (K / 2) + g * (G / 2) + lane * PPL + q, v);
+    }
   }
   if (grad_scale) {
 #pragma unroll
@@ -511,11 +522,12 @@ __global__ void __launch_bounds__(128) rotate_backward_kernel(const T *__restric
 
 template <typename T>
 static int launch_backward_T(const void *y, const void *gout, const void *x, const int16_t *idx, const void *theta, int theta_dtype, const void *scales,
-                             int scales_dtype, void *grad_x, float *grad_theta, float *grad_scale, int64_t M, int K, int krot, int G, cudaStream_t stream) {
+                             int scales_dtype, void *grad_x, float *grad_theta, float *grad_scale, int64_t M, int K, int krot, int G, int ref_formula,
+                             cudaStream_t stream) {
   const int groups = K / G;
   const int64_t row_blocks = (M + 3) / 4;
   // per CTA: 4 warps x krot x G/2 pairs x ({cos, sin} 8 B + slots 4 B + partial 4 B) of dynamic shared memory + the two tiles
-  const size_t dyn = static_cast<size_t>(4) * krot * (G / 2) * 16;
+  const size_t dyn = static_cast<size_t>(4) * krot * (G / 2) * (ref_formula ? 20 : 16);   // (+ 4 B: the g . t sums of the reference's expression)
   const int resident = static_cast<int>((227 * 1024) / (dyn + static_cast<size_t>(8) * G * 16 + 1024));
   const int ctas_per_sm = resident < 1 ? 1 : resident > 6 ? 6 : resident;   // 6: the register limit
   // enough warps to fill the machine, no more splits than row blocks: every warp then walks ~row_blocks / splits blocks of its
@@ -530,11 +542,11 @@ static int launch_backward_T(const void *y, const void *gout, const void *x, con
   if (G == 128) {
     PARO_CUDA_OK(cudaFuncSetAttribute(rotate_backward_kernel<T, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
     rotate_backward_kernel<T, 128><<<static_cast<unsigned>(blocks), 128, dyn, stream>>>(yp, gp, xp, idx, theta, theta_dtype, scales, scales_dtype, gx, grad_theta,
-                                                                                       grad_scale, M, K, krot, static_cast<int>(splits));
+                                                                                       grad_scale, M, K, krot, static_cast<int>(splits), ref_formula);
   } else {
     PARO_CUDA_OK(cudaFuncSetAttribute(rotate_backward_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
     rotate_backward_kernel<T, 64><<<static_cast<unsigned>(blocks), 128, dyn, stream>>>(yp, gp, xp, idx, theta, theta_dtype, scales, scales_dtype, gx, grad_theta,
-                                                                                      grad_scale, M, K, krot, static_cast<int>(splits));
+                                                                                      grad_scale, M, K, krot, static_cast<int>(splits), ref_formula);
   }
   PARO_CUDA_OK(cudaGetLastError());
   note_launches(1);
@@ -543,12 +555,12 @@ static int launch_backward_T(const void *y, const void *gout, const void *x, con
 
 int rotate_backward_launch(const void *y, const void *gout, const void *x, const int16_t *idx, const void *theta, int theta_dtype, const void *scales,
                            int scales_dtype, void *grad_x, float *grad_theta, float *grad_scale, int64_t M, int K, int krot, int G, int dtype,
-                           cudaStream_t stream) {
+                           int ref_formula, cudaStream_t stream) {
   if (M == 0) return PARO_OK;
   switch (dtype) {
-    case PARO_F32: return launch_backward_T<float>(y, gout, x, idx, theta, theta_dtype, scales, scales_dtype, grad_x, grad_theta, grad_scale, M, K, krot, G, stream);
-    case PARO_F16: return launch_backward_T<__half>(y, gout, x, idx, theta, theta_dtype, scales, scales_dtype, grad_x, grad_theta, grad_scale, M, K, krot, G, stream);
-    case PARO_BF16: return launch_backward_T<__nv_bfloat16>(y, gout, x, idx, theta, theta_dtype, scales, scales_dtype, grad_x, grad_theta, grad_scale, M, K, krot, G, stream);
+    case PARO_F32: return launch_backward_T<float>(y, gout, x, idx, theta, theta_dtype, scales, scales_dtype, grad_x, grad_theta, grad_scale, M, K, krot, G, ref_formula, stream);
+    case PARO_F16: return launch_backward_T<__half>(y, gout, x, idx, theta, theta_dtype, scales, scales_dtype, grad_x, grad_theta, grad_scale, M, K, krot, G, ref_formula, stream);
+    case PARO_BF16: return launch_backward_T<__nv_bfloat16>(y, gout, x, idx, theta, theta_dtype, scales, scales_dtype, grad_x, grad_theta, grad_scale, M, K, krot, G, ref_formula, stream);
   }
   set_error("rotate supports Float, Half, and BFloat16, got dtype code %d", dtype);
   return PARO_EINVAL;

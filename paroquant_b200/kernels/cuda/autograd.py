@@ -17,14 +17,19 @@ Deviation from the reference, on purpose: grad_theta here is the gradient (check
 formulation, tests/test_gpu_rotate.py, tests/test_oracle.py).  The reference evaluates
 `(ga*b - gb*a)*cos - (ga*a + gb*b)*sin` (autograd.py:50-52) -- the right expression for the OUTPUT-space gradient and the
 INPUT values of a pair -- after it has un-rotated g as well (autograd.py:38), which makes it return
-`cos * dL/dtheta - sin * sum_rows(g . t)`; `oracle.np_rotate_backward(..., reference_formula=True)` reproduces that value.
-grad_x and grad_scale are the reference's.
+`cos * dL/dtheta - sin * sum_rows(g . t)`.  Setting `REFERENCE_THETA_EXPRESSION = True` (or PARO_ROTATE_BACKWARD=reference in the
+environment) makes the same launch return that value instead, for runs that must reproduce the reference's optimiser
+trajectories; `oracle.np_rotate_backward(..., reference_formula=True)` restates it.  grad_x and grad_scale are the reference's.
 """
 from __future__ import annotations
 
 import torch
 
+import os
+
 from ... import _cabi
+
+REFERENCE_THETA_EXPRESSION = os.environ.get("PARO_ROTATE_BACKWARD", "") == "reference"
 
 
 class RotateTensorFunc(torch.autograd.Function):
@@ -43,7 +48,7 @@ class RotateTensorFunc(torch.autograd.Function):
         K = idx_ij.shape[1]
         flat_scale = None if scale is None else scale.reshape(-1)
         gx, gth, gsc = _cabi.rotate_backward(y.reshape(-1, K), grad_out.reshape(-1, K).to(y.dtype), x.reshape(-1, K), idx_ij, theta,
-                                             flat_scale, ctx.group_size)
+                                             flat_scale, ctx.group_size, reference_formula=REFERENCE_THETA_EXPRESSION)
         grad_x = gx.view_as(x)
         grad_theta = gth.to(theta.dtype)
         grad_scale = None if scale is None else gsc.to(scale.dtype).view_as(scale)

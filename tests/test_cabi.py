@@ -93,21 +93,23 @@ def test_rotate_backward_argument_checks():
     buf = (ctypes.c_char * 8192)()
     p = (ctypes.addressof(buf) + 255) // 256 * 256
     q, g = p + 1024, p + 2048
-    rc = lib.paro_rotate_backward(None, None, None, None, None, 0, None, 0, None, None, None, 1, 128, 8, 128, 0, None)
+    rc = lib.paro_rotate_backward(None, None, None, None, None, 0, None, 0, None, None, None, 1, 128, 8, 128, 0, 0, None)
     assert rc == 1 and b"null pointer" in lib.paro_last_error()
-    rc = lib.paro_rotate_backward(p, p, p, p, p, 0, None, 0, q, g, g, 1, 128, 8, 128, 0, None)        # grad_scale without scales
+    rc = lib.paro_rotate_backward(p, p, p, p, p, 0, None, 0, q, g, g, 1, 128, 8, 128, 0, 0, None)        # grad_scale without scales
     assert rc == 1 and b"grad_scale needs x and scales" in lib.paro_last_error()
-    rc = lib.paro_rotate_backward(p, p, p, p, p, 0, None, 0, p, g, None, 1, 128, 8, 128, 0, None)     # grad_x aliases y
+    rc = lib.paro_rotate_backward(p, p, p, p, p, 0, None, 0, p, g, None, 1, 128, 8, 128, 0, 0, None)     # grad_x aliases y
     assert rc == 1 and b"must not alias" in lib.paro_last_error()
-    rc = lib.paro_rotate_backward(p, p, p, p, p, 0, None, 0, q, g, None, 1, 128, 8, 32, 0, None)
+    rc = lib.paro_rotate_backward(p, p, p, p, p, 0, None, 0, q, g, None, 1, 128, 8, 32, 0, 0, None)
     assert rc == 2 and b"Unsupported group_size: 32; expected 64 or 128" in lib.paro_last_error()
-    rc = lib.paro_rotate_backward(p, p, p, p, p, 0, None, 0, q, g, None, 1, 100, 8, 64, 0, None)
+    rc = lib.paro_rotate_backward(p, p, p, p, p, 0, None, 0, q, g, None, 1, 100, 8, 64, 0, 0, None)
     assert rc == 1 and b"h must be divisible by GROUP_SIZE" in lib.paro_last_error()
-    rc = lib.paro_rotate_backward(p, p, p, p, p, 0, None, 0, q, g, None, 1, 128, 17, 128, 0, None)
+    rc = lib.paro_rotate_backward(p, p, p, p, p, 0, None, 0, q, g, None, 1, 128, 17, 128, 0, 0, None)
     assert rc == 2 and b"Unsupported KROT" in lib.paro_last_error()
-    rc = lib.paro_rotate_backward(p, p, p, p, p, 0, None, 0, q, g, None, 1, 128, 8, 128, 9, None)
+    rc = lib.paro_rotate_backward(p, p, p, p, p, 0, None, 0, q, g, None, 1, 128, 8, 128, 9, 0, None)
     assert rc == 1 and b"Float, Half, and BFloat16" in lib.paro_last_error()
-    rc = lib.paro_rotate_backward(p, p, p, p, p, 0, None, 0, q, g, None, 0, 128, 8, 128, 0, None)     # no rows: no launch, success
+    rc = lib.paro_rotate_backward(p, p, p, p, p, 0, None, 0, q, g, None, 1, 128, 8, 128, 0, 2, None)
+    assert rc == 1 and b"unknown theta_formula" in lib.paro_last_error()
+    rc = lib.paro_rotate_backward(p, p, p, p, p, 0, None, 0, q, g, None, 0, 128, 8, 128, 0, 1, None)     # no rows: no launch, success
     assert rc == 0 and lib.paro_last_launch_count() == 0
 
 

@@ -206,3 +206,28 @@ def test_autograd_group64_bf16_runs_through_the_op(ops):
     ref = 2 * x.detach().float() * sc.detach().float().reshape(-1) ** 2
     assert (x.grad.float() - ref).norm() / ref.norm() < 2e-2
     assert th.grad.float().abs().max() < 0.05 * x.detach().float().square().sum().sqrt()
+
+
+@pytest.mark.parametrize("G", [128, 64])
+def test_fused_backward_vs_oracle_both_theta_formulas(ops, oracle, G):
+    """fp32 kernel against the float64 oracle (oracle.np_rotate_backward, pinned to autograd on the CPU): the gradient, and the
+    value of the reference's expression (autograd.py:50-52 after un-rotating g: cos * gradient - sin * sum_rows(g . t))."""
+    from paroquant_b200 import _cabi
+    K, M = 512, 37
+    L = make_synthetic_layer(K, [64], group_size=G, krot=8, seed=33)
+    pr, th = L.pairs[0].cuda(), L.theta[0].float().cuda()
+    sc = L.channel_scales[0].float().cuda().view(-1)
+    x = torch.randn(M, K, device="cuda")
+    go = torch.randn(M, K, device="cuda")
+    y = torch.ops.rotation.rotate(x, pr, th, sc, G)
+    args = (x.cpu().numpy(), pr.cpu().numpy(), th.cpu().numpy(), y.cpu().numpy(), go.cpu().numpy(), sc.cpu().numpy(), G)
+    for ref in (False, True):
+        gx, gth, gsc = _cabi.rotate_backward(y, go, x, pr, th, sc, G, reference_formula=ref)
+        ox, oth, osc = oracle.np_rotate_backward(*args, reference_formula=ref)
+        # fp32 kernel with MUFU sin / cos against float64: the dense-Jacobian test above sees ~1e-5
+        assert oracle.rel_err(gx.cpu().numpy(), ox) < 5e-5
+        assert oracle.rel_err(gth.cpu().numpy(), oth) < 2e-4, ref
+        assert oracle.rel_err(gsc.cpu().numpy(), osc) < 5e-5
+    a = _cabi.rotate_backward(y, go, x, pr, th, sc, G)[1]
+    b = _cabi.rotate_backward(y, go, x, pr, th, sc, G, reference_formula=True)[1]
+    assert (a - b).norm() / a.norm() > 1e-2          # the two really differ on random data
