@@ -213,6 +213,7 @@ def test_fused_backward_vs_oracle_both_theta_formulas(ops, oracle, G):
     """fp32 kernel against the float64 oracle (oracle.np_rotate_backward, pinned to autograd on the CPU): the gradient, and the
     value of the reference's expression (autograd.py:50-52 after un-rotating g: cos * gradient - sin * sum_rows(g . t))."""
     from paroquant_b200 import _cabi
+    torch.manual_seed(7)
     K, M = 512, 37
     L = make_synthetic_layer(K, [64], group_size=G, krot=8, seed=33)
     pr, th = L.pairs[0].cuda(), L.theta[0].float().cuda()
